@@ -1,0 +1,83 @@
+/*
+ * yastn_b200 — C ABI of the B200-native block-sparse contraction kernels.
+ *
+ * This is the drop-in boundary for YASTN's contraction hot path.  Every entry point takes plain
+ * pointers and sizes (no torch types); device pointers are raw CUDA device addresses, `stream` is a
+ * cudaStream_t passed as void*.  All functions return 0 on success and a negative code on failure;
+ * yb_last_error() returns a thread-local message for the last failure.  Calls are asynchronous on
+ * `stream`, allocate nothing at run time (plans own their device tables) and are CUDA-graph capturable.
+ *
+ * Reference interfaces replaced (paths relative to the yastn tree, commit 60af786a):
+ *   yb_copy_*  : backend.transpose_and_merge  yastn/backend/backend_torch.py:588 (loop: _backend_torch_backwards.py:340-364)
+ *                backend.unmerge              yastn/backend/backend_torch.py:592 (loop: _backend_torch_backwards.py:397-408)
+ *                backend.transpose            yastn/backend/backend_torch.py:584 (loop: _backend_torch_backwards.py:315-319)
+ *                and their backward passes    _backend_torch_backwards.py:325-335, 377-392, 418-426
+ *                prior-art C ABI of the same op: experimental/tm_worker.c:266-297 (tm_worker_parallel_float64/complex128)
+ *   yb_gemm_*  : backend.dot                  yastn/backend/backend_torch.py:549 (loop: _backend_torch_backwards.py:100-109, backward 118-138)
+ *                backend.transpose_dot_sum    yastn/backend/backend_torch.py:553 (loop: _backend_torch_backwards.py:143-157)
+ *                prior art: experimental/torch_mmib.cpp:20-35 ("mm incommensurate batch")
+ *   yb_match_* : pairing of charge sectors    yastn/tensor/_contractions.py:281-298 (_meta_tensordot_f2m), 250-278 (_common_inds);
+ *                single-call boundary         yastn/backend/backend_torch_cpp.py:173-228 (kernel_tensordot_bs)
+ */
+#ifndef YASTN_B200_H
+#define YASTN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YB_ABI_VERSION 1
+
+/* element types */
+#define YB_F64 0
+#define YB_C128 1
+
+/* yb_copy_run flags */
+#define YB_COPY_ZERO_DST 1 /* clear dst before scattering (merge with missing blocks)               */
+#define YB_COPY_CONJ 2     /* complex conjugate while copying (resolves torch's lazy conj bit)        */
+
+/* yb_gemm_run flags */
+#define YB_GEMM_CONJ_A 1
+#define YB_GEMM_CONJ_B 2
+
+typedef struct yb_copy_plan yb_copy_plan;
+typedef struct yb_gemm_plan yb_gemm_plan;
+
+int yb_abi_version(void);
+const char* yb_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Block copy plans.  One record moves one N-d box:  for every index (i_0..i_{rank-1}) with
+ * 0 <= i_k < extent[k]:   dst[dst_base + sum_k i_k*dst_stride[k]] = src[src_base + sum_k i_k*src_stride[k]].
+ * recs is an nrec x (2 + 3*rank) row-major int64 table
+ *     [src_base, dst_base, extent[0..rank), src_stride[0..rank), dst_stride[0..rank)]      (units: elements)
+ * Records must write disjoint destinations.  itemsize is 8 (float64) or 16 (complex128).
+ * ---------------------------------------------------------------------------------------------- */
+int yb_copy_plan_create(const int64_t* recs, int64_t nrec, int rank, int itemsize, int device, yb_copy_plan** out);
+/* info[0]=work items, [1]=elements moved, [2]=records kept after normalisation, [3]=records on the tiled-transpose path */
+int yb_copy_plan_info(const yb_copy_plan* plan, int64_t info[4]);
+int yb_copy_run(const yb_copy_plan* plan, const void* src, void* dst, int64_t dst_elems, int flags, void* stream);
+void yb_copy_plan_destroy(yb_copy_plan* plan);
+
+/* ------------------------------------------------------------------------------------------------
+ * Grouped block GEMM plans.  Problem p computes the M x N block
+ *     C[offC + m*ldc + n] = sum over its segments s of  sum_k opA(A[offA_s + m*sAm_s + k*sAk_s]) * opB(B[offB_s + k*sBk_s + n*sBn_s])
+ * problems: nprob x 6 int64 [M, N, offC, ldc, seg_begin, seg_end)
+ * segments: nseg  x 7 int64 [K, offA, sAm, sAk, offB, sBk, sBn]           (units: elements)
+ * In every segment one of (sAm, sAk) and one of (sBk, sBn) must be 1 (or the extent along it must be 1);
+ * all segments of a plan share the same pair of unit-stride choices.
+ * dtype is YB_F64 or YB_C128.  C blocks of different problems must be disjoint.
+ * ---------------------------------------------------------------------------------------------- */
+int yb_gemm_plan_create(const int64_t* problems, int64_t nprob, const int64_t* segments, int64_t nseg, int dtype,
+                        int device, yb_gemm_plan** out);
+/* info[0]=tiles, [1]=real multiply-adds (M*N*K summed), [2]=64x128 tiles, [3]=64x64 tiles */
+int yb_gemm_plan_info(const yb_gemm_plan* plan, int64_t info[4]);
+int yb_gemm_run(const yb_gemm_plan* plan, const void* A, const void* B, void* C, int flags, void* stream);
+void yb_gemm_plan_destroy(yb_gemm_plan* plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YASTN_B200_H */

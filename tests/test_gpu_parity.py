@@ -1,0 +1,242 @@
+"""GPU parity: the CUDA path, called through the C ABI, against golden vectors recorded from the reference
+and against the CPU oracle.  Bit-exact for data movement; rel. Frobenius error <= 1e-12 for GEMMs
+(the tolerance BASELINE.json's north_star states for float64 / complex128)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import backend_oracle as orc
+from golden_io import small_calls, bench_structs
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+CALLS = small_calls()
+
+
+def _dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def _relerr(out, ref):
+    return np.linalg.norm(out - ref) / max(np.linalg.norm(ref), 1e-300)
+
+
+def _ids(calls):
+    return [f"{c['case']}-{c['policy'][:6]}-{c['dtype']}-{k}" for k, c in enumerate(calls)]
+
+
+@pytest.fixture(scope="module")
+def bk():
+    from yastn_b200 import backend_b200
+    return backend_b200
+
+
+COPY_CALLS = [c for c in CALLS if c["fn"] in ("transpose_and_merge", "unmerge", "transpose")]
+GEMM_CALLS = [c for c in CALLS if c["fn"] in ("dot", "transpose_dot_sum")]
+
+
+@pytest.mark.parametrize("call", COPY_CALLS, ids=_ids(COPY_CALLS))
+def test_copy_functions_bit_exact(bk, call):
+    a = dict(call["args"])
+    data = _dev(a.pop("data"))
+    out = getattr(bk, call["fn"])(data, *a.values())
+    torch.cuda.synchronize()
+    assert out.dtype == data.dtype and out.is_contiguous() and out.data_ptr() != data.data_ptr()
+    assert np.array_equal(out.cpu().numpy(), call["out"])
+
+
+@pytest.mark.parametrize("call", GEMM_CALLS, ids=_ids(GEMM_CALLS))
+def test_gemm_functions(bk, call):
+    a = dict(call["args"])
+    A, B = _dev(a.pop("Adata")), _dev(a.pop("Bdata"))
+    out = getattr(bk, call["fn"])(A, B, *a.values())
+    torch.cuda.synchronize()
+    assert out.cpu().numpy().dtype == call["out"].dtype
+    assert _relerr(out.cpu().numpy(), call["out"]) <= TOL
+
+
+def test_lazy_conj_inputs(bk):
+    """torch's conj bit (backend_torch.conj is lazy, backend_torch.py:264) must be honoured by raw-pointer kernels."""
+    n = 0
+    for call in CALLS:
+        if call["dtype"] != "complex128":
+            continue
+        a = dict(call["args"])
+        if call["fn"] in ("transpose_and_merge", "unmerge", "transpose"):
+            data = a.pop("data")
+            out = getattr(bk, call["fn"])(_dev(data.conj()).conj(), *a.values())   # lazily conjugated twice-stored data
+            ref = getattr(orc, call["fn"])(data, *a.values())
+            assert np.array_equal(out.cpu().numpy(), ref)
+            n += 1
+        elif call["fn"] == "dot":
+            A, B = a.pop("Adata"), a.pop("Bdata")
+            out = bk.dot(_dev(A.conj()).conj(), _dev(B).conj(), *a.values())
+            ref = orc.dot(A, B.conj(), *a.values())
+            assert _relerr(out.cpu().numpy(), ref) <= TOL
+            n += 1
+    assert n > 10
+
+
+def test_backward_matches_oracle_adjoints(bk):
+    rng = np.random.default_rng(7)
+    seen = set()
+    for call in CALLS:
+        fn = call["fn"]
+        key = (fn, call["dtype"], call["policy"])
+        if key in seen:
+            continue
+        seen.add(key)
+        a = dict(call["args"])
+        cplx = call["dtype"] == "complex128"
+
+        def rnd(n):
+            g = rng.standard_normal(n)
+            return g + 1j * rng.standard_normal(n) if cplx else g
+        if fn in ("transpose_and_merge", "unmerge", "transpose"):
+            data = _dev(a.pop("data")).requires_grad_(True)
+            out = getattr(bk, fn)(data, *a.values())
+            G = rnd(out.numel())
+            out.backward(_dev(G))
+            if fn == "transpose_and_merge":
+                ref = orc.transpose_and_merge_backward(G, a["order"], a["meta_new"], a["meta_mrg"], data.numel())
+            elif fn == "unmerge":
+                ref = orc.unmerge_backward(G, a["meta"])
+            else:
+                ref = orc.transpose_backward(G, a["axes"], a["meta_transpose"])
+            assert np.array_equal(data.grad.cpu().numpy(), ref)
+        elif fn == "dot":
+            A0, B0 = a.pop("Adata"), a.pop("Bdata")
+            A, B = _dev(A0).requires_grad_(True), _dev(B0).requires_grad_(True)
+            out = bk.dot(A, B, *a.values())
+            G = rnd(out.numel())
+            out.backward(_dev(G))
+            gA, gB = orc.dot_backward(G, A0, B0, a["meta_dot"])
+            assert _relerr(A.grad.cpu().numpy(), gA) <= TOL
+            assert _relerr(B.grad.cpu().numpy(), gB) <= TOL
+        else:
+            # transpose_dot_sum: compare with torch autograd through the oracle-equivalent dense formula
+            A0, B0 = a.pop("Adata"), a.pop("Bdata")
+            A, B = _dev(A0).requires_grad_(True), _dev(B0).requires_grad_(True)
+            out = bk.transpose_dot_sum(A, B, *a.values())
+            G = rnd(out.numel())
+            out.backward(_dev(G))
+            At, Bt = torch.from_numpy(A0).requires_grad_(True), torch.from_numpy(B0).requires_grad_(True)
+            Am = [At[sl[0]:sl[1]].view(Di).permute(a["Aorder"]).reshape(Dl, Dr) for sl, Di, Dl, Dr in a["Areshape"]]
+            Bm = [Bt[sl[0]:sl[1]].view(Di).permute(a["Border"]).reshape(Dl, Dr) for sl, Di, Dl, Dr in a["Breshape"]]
+            loss = 0
+            Gt = torch.from_numpy(G)
+            for sl, Dslc, pairs in a["meta_dot"]:
+                blk = sum(Am[ia] @ Bm[ib] for ia, ib in pairs)
+                g = Gt[sl[0]:sl[1]].view(Dslc)
+                loss = loss + (blk * g.conj()).sum().real if cplx else loss + (blk * g).sum()
+            loss.backward()
+            assert _relerr(A.grad.cpu().numpy(), At.grad.numpy()) <= TOL
+            assert _relerr(B.grad.cpu().numpy(), Bt.grad.numpy()) <= TOL
+    assert len(seen) >= 10
+
+
+def _run_f2m(bk, A, B, case):
+    st = case["f2m"]
+    ma, mb = st["merge_a"], st["merge_b"]
+    Am = A if ma is None else bk.transpose_and_merge(A, ma["order"], ma["meta_new"], ma["meta_mrg"], ma["Dsize"])
+    Bm = B if mb is None else bk.transpose_and_merge(B, mb["order"], mb["meta_new"], mb["meta_mrg"], mb["Dsize"])
+    C = bk.dot(Am, Bm, st["dot"]["meta_dot"], st["dot"]["Dsize"])
+    if st["unmerge"] is not None:
+        C = bk.unmerge(C, st["unmerge"]["meta"])
+    return C
+
+
+@pytest.mark.parametrize("name", ["U1_D64_P1", "U1_D64_P2", "U1_D64_P3", "U1_D1024_P1", "U1_D1024_P2", "U1_D1024_P3",
+                                  "Z2_D512_P1", "Z2_D512_P2", "U1_D2048_P2", "U1xU1_D4096_P1", "U1xU1_D4096_P2"])
+@pytest.mark.parametrize("dtype", ["float64", "complex128"])
+def test_tensordot_pipeline_vs_oracle(bk, name, dtype):
+    """merge -> dot -> unmerge on benchmark-shaped structures (reference metas) against the CPU oracle."""
+    case = bench_structs()[name]
+    if dtype == "complex128" and case["a"]["size"] > 3_000_000:
+        pytest.skip("oracle too slow")
+    rng = np.random.default_rng(2)
+    A = rng.uniform(-1, 1, case["a"]["size"]); B = rng.uniform(-1, 1, case["b"]["size"])
+    if dtype == "complex128":
+        A = A + 1j * rng.uniform(-1, 1, A.size); B = B + 1j * rng.uniform(-1, 1, B.size)
+    ref = orc.tensordot_f2m(A, B, case)
+    out = _run_f2m(bk, _dev(A), _dev(B), case)
+    torch.cuda.synchronize()
+    assert out.numel() == case["f2m"]["struct_c"]["size"]
+    assert _relerr(out.cpu().numpy(), ref) <= TOL
+
+
+@pytest.mark.parametrize("name", ["U1_D1024_P1", "U1_D1024_P2", "Z2_D512_P1", "U1_D64_P3"])
+def test_policies_agree_on_gpu(bk, name):
+    """fuse_contracted and no_fusion metas recorded from the reference give the same tensor as fuse_to_matrix."""
+    case = bench_structs()[name]
+    rng = np.random.default_rng(4)
+    A = _dev(rng.uniform(-1, 1, case["a"]["size"])); B = _dev(rng.uniform(-1, 1, case["b"]["size"]))
+    ref = _run_f2m(bk, A, B, case).cpu().numpy()
+    st = case["fc"]
+    ma, mb = st["merge_a"], st["merge_b"]
+    Am = A if ma is None else bk.transpose_and_merge(A, ma["order"], ma["meta_new"], ma["meta_mrg"], ma["Dsize"])
+    Bm = B if mb is None else bk.transpose_and_merge(B, mb["order"], mb["meta_new"], mb["meta_mrg"], mb["Dsize"])
+    out = bk.dot(Am, Bm, st["dot"]["meta_dot"], st["dot"]["Dsize"]).cpu().numpy()
+    assert _relerr(out, ref) <= TOL
+    t = case["nf"]["tds"]
+    out = bk.transpose_dot_sum(A, B, t["meta_dot"], t["Areshape"], t["Breshape"], t["Aorder"], t["Border"], t["Dsize"]).cpu().numpy()
+    assert _relerr(out, ref) <= TOL
+
+
+@pytest.mark.parametrize("name", ["U1_D8192_P1", "U1_D16384_P2"])
+def test_full_size_linearity_and_roundtrip(bk, name):
+    """Full benchmark sizes (oracle too slow): size-independent properties.
+    (1) merge followed by its adjoint restores every block that took part; (2) the contraction is linear in A."""
+    case = bench_structs()[name]
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    A = torch.rand(case["a"]["size"], dtype=torch.float64, device="cuda", generator=gen) * 2 - 1
+    A2 = torch.rand(case["a"]["size"], dtype=torch.float64, device="cuda", generator=gen) * 2 - 1
+    B = torch.rand(case["b"]["size"], dtype=torch.float64, device="cuda", generator=gen) * 2 - 1
+    ma = case["f2m"]["merge_a"]
+    if ma is not None:
+        x = A.clone().requires_grad_(True)
+        y = bk.transpose_and_merge(x, ma["order"], ma["meta_new"], ma["meta_mrg"], ma["Dsize"])
+        y.backward(y.detach())
+        assert torch.equal(x.grad, A)          # all blocks take part here: adjoint(merge(A)) == A exactly
+        assert torch.equal(y.sum(), y.sum()) and abs(float(y.detach().abs().sum() - A.abs().sum())) <= 1e-6 * float(A.abs().sum())
+    C1 = _run_f2m(bk, A, B, case)
+    C2 = _run_f2m(bk, A2, B, case)
+    C12 = _run_f2m(bk, A + 0.5 * A2, B, case)
+    err = float(torch.linalg.norm(C12 - (C1 + 0.5 * C2)) / torch.linalg.norm(C12))
+    assert err <= 1e-12
+    # spot-check a few sectors against torch.matmul on the merged operands
+    st = case["f2m"]
+    Am = A if st["merge_a"] is None else bk.transpose_and_merge(A, st["merge_a"]["order"], st["merge_a"]["meta_new"], st["merge_a"]["meta_mrg"], st["merge_a"]["Dsize"])
+    mb = st["merge_b"]
+    Bm = B if mb is None else bk.transpose_and_merge(B, mb["order"], mb["meta_new"], mb["meta_mrg"], mb["Dsize"])
+    Cm = bk.dot(Am, Bm, st["dot"]["meta_dot"], st["dot"]["Dsize"])
+    for rec in st["dot"]["meta_dot"][:: max(1, len(st["dot"]["meta_dot"]) // 5)]:
+        slc, Dc, sla, Da, slb, Db = rec
+        ref = Am[sla[0]:sla[1]].view(Da) @ Bm[slb[0]:slb[1]].view(Db)
+        got = Cm[slc[0]:slc[1]].view(Dc)
+        assert float(torch.linalg.norm(got - ref) / torch.linalg.norm(ref)) <= 1e-12
+
+
+def test_rejects_cpu_and_unsupported_inputs(bk):
+    case = bench_structs()["U1_D64_P1"]
+    st = case["f2m"]["dot"]
+    with pytest.raises(TypeError):
+        bk.dot(torch.zeros(10, dtype=torch.float64), torch.zeros(10, dtype=torch.float64), st["meta_dot"], st["Dsize"])
+    with pytest.raises(TypeError):
+        bk.dot(torch.zeros(10, dtype=torch.float32, device="cuda"), torch.zeros(10, dtype=torch.float32, device="cuda"), st["meta_dot"], st["Dsize"])
+
+
+def test_empty_and_degenerate(bk):
+    # empty result (tests/tensor/test_tensordot.py:161-163 in the reference): no records, Dsize 0
+    out = bk.dot(torch.zeros(6, dtype=torch.float64, device="cuda"), torch.zeros(20, dtype=torch.float64, device="cuda"), (), 0)
+    assert out.numel() == 0
+    out = bk.transpose_and_merge(torch.zeros(6, dtype=torch.float64, device="cuda"), (0, 1), (), (), 0)
+    assert out.numel() == 0
+    # 1x1x1 problem and K = 1 outer product
+    A = _dev(np.array([3.0])); B = _dev(np.array([-2.0]))
+    out = bk.dot(A, B, (((0, 1), (1, 1), (0, 1), (1, 1), (0, 1), (1, 1)),), 1)
+    assert out.cpu().numpy().tolist() == [-6.0]
+    a = np.arange(1, 6, dtype=np.float64); b = np.arange(1, 8, dtype=np.float64)
+    out = bk.dot(_dev(a), _dev(b), (((0, 35), (5, 7), (0, 5), (5, 1), (0, 7), (1, 7)),), 35)
+    assert np.array_equal(out.cpu().numpy(), np.outer(a, b).reshape(-1))

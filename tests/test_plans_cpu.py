@@ -1,0 +1,122 @@
+"""Host logic (no GPU): the int64 tables built by yastn_b200.plans reproduce the oracle on every recorded call."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import backend_oracle as orc
+from golden_io import small_calls, bench_structs
+from table_exec import exec_copy, exec_gemm
+from yastn_b200 import plans, _lib
+
+CALLS = small_calls()
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _sel(fn):
+    return [c for c in CALLS if c["fn"] == fn]
+
+
+@pytest.mark.parametrize("call", _sel("transpose_and_merge"), ids=lambda c: f"{c['case']}-{c['policy'][:6]}-{c['dtype']}")
+def test_merge_records(call):
+    a = call["args"]
+    recs, rank, covered = plans.merge_records(a["order"], a["meta_new"], a["meta_mrg"])
+    out = exec_copy(recs, rank, a["data"], np.zeros(a["Dsize"], dtype=a["data"].dtype))
+    assert np.array_equal(out, call["out"])
+    assert covered == sum(int(np.prod(m[2])) for m in a["meta_mrg"])
+    # adjoint records gather the same elements back
+    back = exec_copy(plans.reverse_records(recs, rank), rank, out, np.zeros_like(a["data"]))
+    assert np.array_equal(back, orc.transpose_and_merge_backward(out, a["order"], a["meta_new"], a["meta_mrg"], a["data"].size))
+
+
+@pytest.mark.parametrize("call", _sel("unmerge"), ids=lambda c: f"{c['case']}-{c['dtype']}")
+def test_unmerge_records(call):
+    a = call["args"]
+    recs, rank = plans.unmerge_records(a["meta"])
+    out = exec_copy(recs, rank, a["data"], np.full_like(a["data"], np.nan))
+    assert np.array_equal(out, call["out"])
+
+
+@pytest.mark.parametrize("call", _sel("transpose"), ids=lambda c: f"{c['case']}-{c['dtype']}")
+def test_transpose_records(call):
+    a = call["args"]
+    recs, rank = plans.transpose_records(a["axes"], a["meta_transpose"])
+    out = exec_copy(recs, rank, a["data"], np.full_like(a["data"], np.nan))
+    assert np.array_equal(out, call["out"])
+
+
+@pytest.mark.parametrize("call", _sel("dot"), ids=lambda c: f"{c['case']}-{c['policy'][:6]}-{c['dtype']}")
+def test_dot_tables(call):
+    a = call["args"]
+    problems, segments = plans.dot_tables(a["meta_dot"])
+    A, B = a["Adata"], a["Bdata"]
+    dt = np.promote_types(A.dtype, B.dtype)
+    out = exec_gemm(problems, segments, A.astype(dt), B.astype(dt), np.zeros(a["Dsize"], dtype=dt))
+    assert np.linalg.norm(out - call["out"]) <= 1e-13 * max(1.0, np.linalg.norm(call["out"]))
+    # backward tables against the oracle adjoint
+    rng = np.random.default_rng(3)
+    G = rng.standard_normal(a["Dsize"]).astype(dt)
+    if dt.kind == "c":
+        G = G + 1j * rng.standard_normal(a["Dsize"])
+    gA_ref, gB_ref = orc.dot_backward(G, A.astype(dt), B.astype(dt), a["meta_dot"])
+    pa, sa, pb, sb = plans.dot_backward_tables(a["meta_dot"])
+    gA = exec_gemm(pa, sa, G, B.astype(dt), np.zeros(A.size, dtype=dt), conj_b=True)
+    gB = exec_gemm(pb, sb, A.astype(dt), G, np.zeros(B.size, dtype=dt), conj_a=True)
+    assert np.linalg.norm(gA - gA_ref) <= 1e-12 * max(1.0, np.linalg.norm(gA_ref))
+    assert np.linalg.norm(gB - gB_ref) <= 1e-12 * max(1.0, np.linalg.norm(gB_ref))
+
+
+@pytest.mark.parametrize("call", _sel("transpose_dot_sum"), ids=lambda c: f"{c['case']}-{c['dtype']}")
+def test_tds_tables(call):
+    a = call["args"]
+    problems, segments, pack_a, pack_b = plans.tds_tables(a["meta_dot"], a["Areshape"], a["Breshape"], a["Aorder"], a["Border"])
+    A, B = a["Adata"], a["Bdata"]
+    dt = np.promote_types(A.dtype, B.dtype)
+    A, B = A.astype(dt), B.astype(dt)
+    if pack_a:
+        recs, rank = plans.pack_records(a["Areshape"], a["Aorder"])
+        A = exec_copy(recs, rank, A, np.zeros_like(A))
+    if pack_b:
+        recs, rank = plans.pack_records(a["Breshape"], a["Border"])
+        B = exec_copy(recs, rank, B, np.zeros_like(B))
+    out = exec_gemm(problems, segments, A, B, np.zeros(a["Dsize"], dtype=dt))
+    assert np.linalg.norm(out - call["out"]) <= 1e-13 * max(1.0, np.linalg.norm(call["out"]))
+
+
+def test_bench_struct_tables_small():
+    """Structure fixtures at benchmark shapes: tables execute to the oracle result (small D only on CPU)."""
+    for name in ("U1_D64_P1", "U1_D64_P2", "U1_D64_P3"):
+        case = bench_structs()[name]
+        rng = np.random.default_rng(5)
+        A = rng.standard_normal(case["a"]["size"]); B = rng.standard_normal(case["b"]["size"])
+        ref = orc.tensordot_f2m(A, B, case)
+        st = case["f2m"]
+        Am, Bm = A, B
+        for side, key in (("a", "merge_a"), ("b", "merge_b")):
+            m = st[key]
+            if m is not None:
+                recs, rank, _ = plans.merge_records(m["order"], m["meta_new"], m["meta_mrg"])
+                res = exec_copy(recs, rank, A if side == "a" else B, np.zeros(m["Dsize"]))
+                if side == "a":
+                    Am = res
+                else:
+                    Bm = res
+        problems, segments = plans.dot_tables(st["dot"]["meta_dot"])
+        C = exec_gemm(problems, segments, Am, Bm, np.zeros(st["dot"]["Dsize"]))
+        if st["unmerge"] is not None:
+            recs, rank = plans.unmerge_records(st["unmerge"]["meta"])
+            C = exec_copy(recs, rank, C, np.zeros_like(C))
+        assert np.linalg.norm(C - ref) <= 1e-12 * np.linalg.norm(ref)
+
+
+def test_library_exports_every_declared_symbol():
+    """The C-ABI library loads on a CPU-only box and exports every function include/yastn_b200.h declares."""
+    header = open(os.path.join(ROOT, "include", "yastn_b200.h")).read()
+    declared = set(re.findall(r"\b(yb_[a-z0-9_]+)\s*\(", header))
+    lib = _lib.load()
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(lib, name), f"libyastn_b200.so does not export {name}"
+    assert declared == set(_lib.SIGNATURES), "ctypes signature table out of sync with the header"
+    assert lib.yb_abi_version() == 1

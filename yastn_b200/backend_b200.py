@@ -1,0 +1,379 @@
+"""Drop-in replacements for the hot functions of ``yastn.backend.backend_torch`` on B200.
+
+Same names, argument meaning and return contract as the reference backend
+(yastn/backend/backend_torch.py:549-593; loops in yastn/backend/_backend_torch_backwards.py):
+
+    transpose_and_merge(data, order, meta_new, meta_mrg, Dsize) -> Tensor[Dsize]
+    dot(Adata, Bdata, meta_dot, Dsize)                            -> Tensor[Dsize]
+    unmerge(data, meta)                                           -> Tensor[len(data)]
+    transpose(data, axes, meta_transpose)                         -> Tensor[len(data)]
+    transpose_dot_sum(Adata, Bdata, meta_dot, Areshape, Breshape, Aorder, Border, Dsize) -> Tensor[Dsize]
+
+Inputs are borrowed and never mutated, outputs are freshly allocated 1-D contiguous CUDA tensors, every
+function is differentiable (explicit backward, like the reference's autograd.Functions) and each forward is
+ONE kernel launch through the C ABI (include/yastn_b200.h) instead of a Python loop over blocks.
+Only CUDA float64 / complex128 tensors are accepted: there is no CPU or eager-torch fallback.
+
+Use with YASTN either as ``yastn.make_config(backend=yastn_b200.backend_b200.as_yastn_backend(), ...)`` or by
+``activate()`` which rebinds the five functions on ``yastn.backend.backend_torch``.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib, plans
+
+BACKEND_ID = "torch"   # serialised tensors stay combinable with the stock torch backend
+
+_CACHE = plans.PlanCache()
+_DTYPE_CODE = {torch.float64: _lib.YB_F64, torch.complex128: _lib.YB_C128}
+_ITEMSIZE = {torch.float64: 8, torch.complex128: 16}
+
+
+def clear_plan_cache():
+    _CACHE.clear()
+
+
+def plan_cache_stats():
+    return {"hits": _CACHE.hits, "misses": _CACHE.misses, "size": len(_CACHE._d)}
+
+
+def _check(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError(f"yastn_b200.{name}: expected a CUDA tensor (no CPU fallback), got {type(t).__name__}"
+                        f"{'' if not isinstance(t, torch.Tensor) else ' on ' + str(t.device)}")
+    if t.dtype not in _DTYPE_CODE:
+        raise TypeError(f"yastn_b200.{name}: dtype {t.dtype} not supported (float64 / complex128 only)")
+    if t.dim() != 1:
+        raise ValueError(f"yastn_b200.{name}: data must be 1-D")
+
+
+def _raw(t):
+    """(tensor to keep alive, conj flag): contiguous storage view of t; lazy conj is resolved inside the kernels."""
+    conj = t.is_conj()
+    if conj:
+        t = t.conj()          # flips the bit back: a view of the physical (un-conjugated) storage
+    if not t.is_contiguous():
+        t = t.contiguous()
+    return t, conj
+
+
+def _stream(dev):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _run_copy(plan, src, dst, zero):
+    raw, conj = _raw(src)
+    flags = (_lib.YB_COPY_ZERO_DST if zero else 0) | (_lib.YB_COPY_CONJ if conj else 0)
+    dev = src.device
+    if torch.cuda.current_device() != dev.index:
+        with torch.cuda.device(dev):
+            plan.run(raw.data_ptr(), dst.data_ptr(), dst.numel(), flags, _stream(dev))
+    else:
+        plan.run(raw.data_ptr(), dst.data_ptr(), dst.numel(), flags, _stream(dev))
+
+
+def _run_gemm(plan, A, B, C, conj_a=False, conj_b=False):
+    ra, ca = _raw(A)
+    rb, cb = _raw(B)
+    flags = (_lib.YB_GEMM_CONJ_A if (ca != conj_a) else 0) | (_lib.YB_GEMM_CONJ_B if (cb != conj_b) else 0)
+    dev = C.device
+    if torch.cuda.current_device() != dev.index:
+        with torch.cuda.device(dev):
+            plan.run(ra.data_ptr(), rb.data_ptr(), C.data_ptr(), flags, _stream(dev))
+    else:
+        plan.run(ra.data_ptr(), rb.data_ptr(), C.data_ptr(), flags, _stream(dev))
+
+
+# -------------------------------------------------------------------------------------------------
+# plan lookup (cached on the identity of YASTN's lru-cached meta objects)
+# -------------------------------------------------------------------------------------------------
+
+def _merge_plans(data, order, meta_new, meta_mrg, Dsize):
+    key = ("mrg", id(meta_mrg), tuple(order), Dsize, len(meta_new), data.dtype, data.device.index)
+
+    def build():
+        recs, rank, covered = plans.merge_records(order, meta_new, meta_mrg)
+        fwd = plans.CopyPlan(recs, rank, _ITEMSIZE[data.dtype], data.device.index, covered)
+        return {"fwd": fwd, "recs": recs, "rank": rank, "bwd": None}
+    return _CACHE.get(key, meta_mrg, build)
+
+
+def _unmerge_plans(data, meta):
+    key = ("unm", id(meta), data.dtype, data.device.index)
+
+    def build():
+        recs, rank = plans.unmerge_records(meta)
+        return {"fwd": plans.CopyPlan(recs, rank, _ITEMSIZE[data.dtype], data.device.index), "recs": recs, "rank": rank, "bwd": None}
+    return _CACHE.get(key, meta, build)
+
+
+def _transpose_plans(data, axes, meta):
+    key = ("trn", id(meta), tuple(axes), data.dtype, data.device.index)
+
+    def build():
+        recs, rank = plans.transpose_records(axes, meta)
+        return {"fwd": plans.CopyPlan(recs, rank, _ITEMSIZE[data.dtype], data.device.index), "recs": recs, "rank": rank, "bwd": None}
+    return _CACHE.get(key, meta, build)
+
+
+def _bwd_copy_plan(ent, dtype, device):
+    if ent["bwd"] is None:
+        ent["bwd"] = plans.CopyPlan(plans.reverse_records(ent["recs"], ent["rank"]), ent["rank"], _ITEMSIZE[dtype], device)
+    return ent["bwd"]
+
+
+def _dot_plans(meta_dot, dtype, device):
+    key = ("dot", id(meta_dot), dtype, device)
+
+    def build():
+        problems, segments = plans.dot_tables(meta_dot)
+        return {"fwd": plans.GemmPlan(problems, segments, _DTYPE_CODE[dtype], device), "bwd": None}
+    return _CACHE.get(key, meta_dot, build)
+
+
+# -------------------------------------------------------------------------------------------------
+# autograd functions (forward = one launch; backward = adjoint plan)
+# -------------------------------------------------------------------------------------------------
+
+class _TransposeAndMerge(torch.autograd.Function):
+    @staticmethod
+    def forward(data, order, meta_new, meta_mrg, Dsize):
+        ent = _merge_plans(data, order, meta_new, meta_mrg, Dsize)
+        out = torch.empty(Dsize, dtype=data.dtype, device=data.device)
+        _run_copy(ent["fwd"], data, out, zero=ent["fwd"].covered < Dsize)
+        return out
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        data, order, meta_new, meta_mrg, Dsize = inputs
+        ctx.args = (order, meta_new, meta_mrg, Dsize)
+        ctx.n_src = data.numel()
+
+    @staticmethod
+    def backward(ctx, grad):
+        order, meta_new, meta_mrg, Dsize = ctx.args
+        grad = grad.resolve_conj() if grad.is_conj() else grad
+        ent = _merge_plans(grad, order, meta_new, meta_mrg, Dsize)
+        plan = _bwd_copy_plan(ent, grad.dtype, grad.device.index)
+        out = torch.empty(ctx.n_src, dtype=grad.dtype, device=grad.device)
+        _run_copy(plan, grad, out, zero=ent["fwd"].covered < ctx.n_src)
+        return out, None, None, None, None
+
+
+class _Unmerge(torch.autograd.Function):
+    @staticmethod
+    def forward(data, meta):
+        ent = _unmerge_plans(data, meta)
+        out = torch.empty(data.numel(), dtype=data.dtype, device=data.device)
+        _run_copy(ent["fwd"], data, out, zero=False)
+        return out
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        ctx.meta = inputs[1]
+
+    @staticmethod
+    def backward(ctx, grad):
+        ent = _unmerge_plans(grad, ctx.meta)
+        plan = _bwd_copy_plan(ent, grad.dtype, grad.device.index)
+        out = torch.empty(grad.numel(), dtype=grad.dtype, device=grad.device)
+        _run_copy(plan, grad, out, zero=False)
+        return out, None
+
+
+class _Transpose(torch.autograd.Function):
+    @staticmethod
+    def forward(data, axes, meta_transpose):
+        ent = _transpose_plans(data, axes, meta_transpose)
+        out = torch.empty(data.numel(), dtype=data.dtype, device=data.device)
+        _run_copy(ent["fwd"], data, out, zero=False)
+        return out
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        ctx.args = inputs[1:]
+
+    @staticmethod
+    def backward(ctx, grad):
+        axes, meta = ctx.args
+        ent = _transpose_plans(grad, axes, meta)
+        plan = _bwd_copy_plan(ent, grad.dtype, grad.device.index)
+        out = torch.empty(grad.numel(), dtype=grad.dtype, device=grad.device)
+        _run_copy(plan, grad, out, zero=False)
+        return out, None, None
+
+
+def _promote(Adata, Bdata):
+    dtype = torch.promote_types(Adata.dtype, Bdata.dtype)
+    if Adata.dtype != dtype:
+        Adata = Adata.to(dtype)
+    if Bdata.dtype != dtype:
+        Bdata = Bdata.to(dtype)
+    return Adata, Bdata, dtype
+
+
+class _Dot(torch.autograd.Function):
+    @staticmethod
+    def forward(Adata, Bdata, meta_dot, Dsize):
+        Adata, Bdata, dtype = _promote(Adata, Bdata)
+        ent = _dot_plans(meta_dot, dtype, Adata.device.index)
+        # every element of C is written by exactly one GEMM: no zero fill needed
+        out = torch.empty(Dsize, dtype=dtype, device=Adata.device)
+        _run_gemm(ent["fwd"], Adata, Bdata, out)
+        return out
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        Adata, Bdata, meta_dot, Dsize = inputs
+        ctx.save_for_backward(Adata, Bdata)
+        ctx.meta_dot = meta_dot
+
+    @staticmethod
+    def backward(ctx, grad):
+        Adata, Bdata = ctx.saved_tensors
+        in_dtypes = (Adata.dtype, Bdata.dtype)
+        Adata, Bdata, dtype = _promote(Adata, Bdata)
+        if grad.dtype != dtype:
+            grad = grad.to(dtype)
+        dev = Adata.device.index
+        ent = _dot_plans(ctx.meta_dot, dtype, dev)
+        if ent["bwd"] is None:
+            pa, sa, pb, sb = plans.dot_backward_tables(ctx.meta_dot)
+            ent["bwd"] = (plans.GemmPlan(pa, sa, _DTYPE_CODE[dtype], dev), plans.GemmPlan(pb, sb, _DTYPE_CODE[dtype], dev))
+        plan_a, plan_b = ent["bwd"]
+        # blocks of A / B that take part in no product keep a zero gradient
+        gA = torch.zeros(Adata.numel(), dtype=dtype, device=Adata.device)
+        gB = torch.zeros(Bdata.numel(), dtype=dtype, device=Bdata.device)
+        _run_gemm(plan_a, grad, Bdata, gA, conj_b=True)     # A_b = C_b @ B^H
+        _run_gemm(plan_b, Adata, grad, gB, conj_a=True)     # B_b = A^H @ C_b
+        if in_dtypes[0] != dtype:
+            gA = gA.real.to(in_dtypes[0]) if not in_dtypes[0].is_complex else gA.to(in_dtypes[0])
+        if in_dtypes[1] != dtype:
+            gB = gB.real.to(in_dtypes[1]) if not in_dtypes[1].is_complex else gB.to(in_dtypes[1])
+        return gA, gB, None, None
+
+
+def _tds_plans(meta_dot, Areshape, Breshape, Aorder, Border, dtype, device):
+    key = ("tds", id(meta_dot), id(Areshape), id(Breshape), tuple(Aorder), tuple(Border), dtype, device)
+
+    def build():
+        problems, segments, pack_a, pack_b = plans.tds_tables(meta_dot, Areshape, Breshape, Aorder, Border)
+        ent = {"gemm": plans.GemmPlan(problems, segments, _DTYPE_CODE[dtype], device), "pack_a": None, "pack_b": None,
+               "refs": (Areshape, Breshape)}   # keep the ids used in the key alive
+        if pack_a:
+            recs, rank = plans.pack_records(Areshape, Aorder)
+            ent["pack_a"] = plans.CopyPlan(recs, rank, _ITEMSIZE[dtype], device)
+        if pack_b:
+            recs, rank = plans.pack_records(Breshape, Border)
+            ent["pack_b"] = plans.CopyPlan(recs, rank, _ITEMSIZE[dtype], device)
+        return ent
+    return _CACHE.get(key, meta_dot, build)
+
+
+def _tds_forward(Adata, Bdata, meta_dot, Areshape, Breshape, Aorder, Border, Dsize):
+    Adata, Bdata, dtype = _promote(Adata, Bdata)
+    ent = _tds_plans(meta_dot, Areshape, Breshape, Aorder, Border, dtype, Adata.device.index)
+    if ent["pack_a"] is not None:
+        packed = torch.empty(Adata.numel(), dtype=dtype, device=Adata.device)
+        _run_copy(ent["pack_a"], Adata, packed, zero=False)   # blocks not taking part stay uninitialised and unread
+        Adata = packed
+    if ent["pack_b"] is not None:
+        packed = torch.empty(Bdata.numel(), dtype=dtype, device=Bdata.device)
+        _run_copy(ent["pack_b"], Bdata, packed, zero=False)
+        Bdata = packed
+    out = torch.empty(Dsize, dtype=dtype, device=Adata.device)
+    _run_gemm(ent["gemm"], Adata, Bdata, out)
+    return out
+
+
+class _TransposeDotSum(torch.autograd.Function):
+    @staticmethod
+    def forward(Adata, Bdata, meta_dot, Areshape, Breshape, Aorder, Border, Dsize):
+        return _tds_forward(Adata, Bdata, meta_dot, Areshape, Breshape, Aorder, Border, Dsize)
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        ctx.save_for_backward(inputs[0], inputs[1])
+        ctx.args = inputs[2:]
+
+    @staticmethod
+    def backward(ctx, grad):
+        # adjoint through explicit packing: At_b = C_b @ Bt^H, Bt_b = At^H @ C_b, then un-permute
+        Adata, Bdata = ctx.saved_tensors
+        meta_dot, Areshape, Breshape, Aorder, Border, Dsize = ctx.args
+        in_dtypes = (Adata.dtype, Bdata.dtype)
+        Adata, Bdata, dtype = _promote(Adata, Bdata)
+        grad = grad.to(dtype) if grad.dtype != dtype else grad
+        dev = Adata.device
+        key = ("tdsb", id(meta_dot), id(Areshape), id(Breshape), tuple(Aorder), tuple(Border), dtype, dev.index)
+
+        def build():
+            ra, rka = plans.pack_records(Areshape, Aorder)
+            rb, rkb = plans.pack_records(Breshape, Border)
+            # packed-layout forward meta: C[sl] = sum_pairs At[ia] (Dl x K) @ Bt[ib] (K x Dr)
+            recs = []
+            for (sl, (Dl, Dr), pairs) in meta_dot:
+                for ia, ib in pairs:
+                    sla, _, _, K = Areshape[ia]
+                    slb = Breshape[ib][0]
+                    recs.append((sl, (Dl, Dr), sla, (Dl, K), slb, (K, Dr)))
+            pa, sa, pb, sb = plans.dot_backward_tables(recs)
+            isz, code = _ITEMSIZE[dtype], _DTYPE_CODE[dtype]
+            return {"pack_a": plans.CopyPlan(ra, rka, isz, dev.index), "pack_b": plans.CopyPlan(rb, rkb, isz, dev.index),
+                    "unpack_a": plans.CopyPlan(plans.reverse_records(ra, rka), rka, isz, dev.index),
+                    "unpack_b": plans.CopyPlan(plans.reverse_records(rb, rkb), rkb, isz, dev.index),
+                    "ga": plans.GemmPlan(pa, sa, code, dev.index), "gb": plans.GemmPlan(pb, sb, code, dev.index)}
+        ent = _CACHE.get(key, meta_dot, build)
+        At = torch.zeros(Adata.numel(), dtype=dtype, device=dev)
+        Bt = torch.zeros(Bdata.numel(), dtype=dtype, device=dev)
+        _run_copy(ent["pack_a"], Adata, At, zero=False)
+        _run_copy(ent["pack_b"], Bdata, Bt, zero=False)
+        gAt = torch.zeros(Adata.numel(), dtype=dtype, device=dev)
+        gBt = torch.zeros(Bdata.numel(), dtype=dtype, device=dev)
+        _run_gemm(ent["ga"], grad, Bt, gAt, conj_b=True)
+        _run_gemm(ent["gb"], At, grad, gBt, conj_a=True)
+        gA = torch.zeros(Adata.numel(), dtype=dtype, device=dev)
+        gB = torch.zeros(Bdata.numel(), dtype=dtype, device=dev)
+        _run_copy(ent["unpack_a"], gAt, gA, zero=False)
+        _run_copy(ent["unpack_b"], gBt, gB, zero=False)
+        if in_dtypes[0] != dtype:
+            gA = gA.real.to(in_dtypes[0]) if not in_dtypes[0].is_complex else gA.to(in_dtypes[0])
+        if in_dtypes[1] != dtype:
+            gB = gB.real.to(in_dtypes[1]) if not in_dtypes[1].is_complex else gB.to(in_dtypes[1])
+        return gA, gB, None, None, None, None, None, None
+
+
+# -------------------------------------------------------------------------------------------------
+# public backend functions (names and signatures of yastn.backend.backend_torch)
+# -------------------------------------------------------------------------------------------------
+
+def transpose_and_merge(data, order, meta_new, meta_mrg, Dsize):
+    _check(data, "transpose_and_merge")
+    return _TransposeAndMerge.apply(data, order, meta_new, meta_mrg, Dsize)
+
+
+def unmerge(data, meta):
+    _check(data, "unmerge")
+    return _Unmerge.apply(data, meta)
+
+
+def transpose(data, axes, meta_transpose):
+    _check(data, "transpose")
+    return _Transpose.apply(data, axes, meta_transpose)
+
+
+def dot(Adata, Bdata, meta_dot, Dsize):
+    _check(Adata, "dot")
+    _check(Bdata, "dot")
+    return _Dot.apply(Adata, Bdata, meta_dot, Dsize)
+
+
+def transpose_dot_sum(Adata, Bdata, meta_dot, Areshape, Breshape, Aorder, Border, Dsize):
+    _check(Adata, "transpose_dot_sum")
+    _check(Bdata, "transpose_dot_sum")
+    return _TransposeDotSum.apply(Adata, Bdata, meta_dot, Areshape, Breshape, Aorder, Border, Dsize)
+
+
+HOT_FUNCTIONS = ("transpose_and_merge", "unmerge", "transpose", "dot", "transpose_dot_sum")
