@@ -1,0 +1,276 @@
+"""Drop-in tests: the real YASTN drives our backend module; results against YASTN's stock numpy backend.
+
+Block structure (struct, slices, hfs, mfs, trans) must be equal tuple-for-tuple ("bit-exact metadata", north_star),
+data within rel. Frobenius error 1e-12.  Two variants of every test:
+  * ``shim`` (CPU, not marked gpu): the device side of the C ABI is replaced by the numpy table interpreter
+    (tests/cpu_shim.py), so only the host logic is under test — plan tables, caching, promotion, conj, autograd;
+  * ``cuda`` (marked gpu): the real kernels on the B200 through the C ABI.
+The test bodies mirror the reference's own tests (tests/tensor/test_tensordot.py:29-60 ``tensordot_vs_numpy``,
+test_fuse_hard.py, test_transpose.py, test_ncon_einsum.py, tests/mps/test_dmrg.py).
+"""
+import numpy as np
+import pytest
+import torch
+
+from yastn_loader import load_yastn
+
+yastn = load_yastn()
+if yastn is None:
+    pytest.skip("yastn not importable (no baseline/_ref, no reference checkout)", allow_module_level=True)
+
+from yastn_b200 import yastn_backend  # noqa: E402
+import cpu_shim  # noqa: E402
+
+TOL = 1e-12
+POLICIES = ("fuse_to_matrix", "fuse_contracted", "no_fusion")
+
+
+@pytest.fixture(params=["shim", pytest.param("cuda", marks=pytest.mark.gpu)])
+def device(request):
+    if request.param == "shim":
+        cpu_shim.install()
+        yield "cpu"
+        cpu_shim.uninstall()
+    else:
+        cpu_shim.uninstall()
+        assert torch.cuda.is_available()
+        yield "cuda"
+
+
+def cfgs(sym, policy, device, fusion="hard"):
+    """(reference config on the numpy backend, our config) with otherwise identical settings."""
+    ref = yastn.make_config(sym=sym, backend="np", tensordot_policy=policy, default_fusion=fusion)
+    our = yastn.make_config(sym=sym, backend=yastn_backend.module(), tensordot_policy=policy, default_fusion=fusion,
+                            default_device=device)
+    return ref, our
+
+
+def mirror(x, cfg):
+    """Same tensor (identical bits) on another config."""
+    return yastn.Tensor.from_dict(x.to_dict(level=2), config=cfg)
+
+
+def same_structure(c, r):
+    assert c.struct == r.struct
+    assert c.slices == r.slices
+    assert c.hfs == r.hfs and c.mfs == r.mfs and c.trans == r.trans
+    assert c.is_consistent()
+
+
+def close(c, r, tol=TOL):
+    same_structure(c, r)
+    x = c.to_numpy() if c.size else np.zeros(0)
+    y = r.to_numpy() if r.size else np.zeros(0)
+    nrm = np.linalg.norm(y)
+    assert np.linalg.norm(x - y) <= tol * max(nrm, 1e-300) or (nrm == 0 and np.linalg.norm(x) == 0)
+
+
+def u1_operands(cfg, dtype):
+    a = yastn.rand(config=cfg, s=(-1, 1, 1, -1), t=((-1, 1, 2), (-1, 1, 2), (-1, 1, 2), (-1, 1, 2)),
+                   D=((1, 2, 3), (4, 5, 6), (7, 8, 9), (10, 11, 12)), dtype=dtype)
+    b = yastn.rand(config=cfg, s=(1, -1, 1), t=((-1, 1, 2), (-1, 1, 2), (-1, 0, 1)),
+                   D=((1, 2, 3), (4, 5, 6), (10, 7, 11)), dtype=dtype)
+    return a, b
+
+
+@pytest.mark.parametrize("policy", POLICIES)
+@pytest.mark.parametrize("dtype", ["float64", "complex128"])
+def test_tensordot_u1(device, policy, dtype):
+    ref, our = cfgs("U1", policy, device)
+    ref.backend.random_seed(3)
+    a, b = u1_operands(ref, dtype)
+    A, B = mirror(a, our), mirror(b, our)
+    before = yastn_backend.call_counts()["native"]["dot"] + yastn_backend.call_counts()["native"]["transpose_dot_sum"]
+    for axes, conj in ((((0, 1), (0, 1)), (0, 0)), ((0, 0), (0, 0)), (((1, 0), (1, 0)), (1, 1)), (((), ()), (0, 0)),
+                       (((0, 1), (0, 1)), (1, 0)), (((0, 1), (0, 1)), (0, 1))):
+        if conj in ((1, 0), (0, 1)):
+            # signatures must match after conjugating one side: contract a with conj(a)-like partner
+            r = yastn.tensordot(a, a, axes=((0, 1, 2), (0, 1, 2)), conj=conj)
+            c = yastn.tensordot(A, A, axes=((0, 1, 2), (0, 1, 2)), conj=conj)
+        else:
+            r = yastn.tensordot(a, b, axes=axes, conj=conj)
+            c = yastn.tensordot(A, B, axes=axes, conj=conj)
+        close(c, r)
+        assert yastn.are_independent(c, A) and yastn.are_independent(c, B)
+    # lazy transposes folded into the merge order
+    r = yastn.tensordot(a.transpose((3, 1, 0, 2)), b.transpose((2, 0, 1)), axes=((2, 1), (1, 2)))
+    c = yastn.tensordot(A.transpose((3, 1, 0, 2)), B.transpose((2, 0, 1)), axes=((2, 1), (1, 2)))
+    close(c, r)
+    after = yastn_backend.call_counts()["native"]["dot"] + yastn_backend.call_counts()["native"]["transpose_dot_sum"]
+    assert after - before >= 7      # every contraction went through our functions
+
+
+@pytest.mark.parametrize("policy", POLICIES)
+@pytest.mark.parametrize("sym", ["dense", "Z2", "U1xU1", "Z2xU1"])
+def test_tensordot_other_symmetries(device, policy, sym):
+    symarg = {"Z2xU1": yastn.sym.sym_Z2xU1, "dense": "dense"}.get(sym, sym)
+    ref, our = cfgs(symarg, policy, device)
+    ref.backend.random_seed(5)
+    if sym == "dense":
+        a = yastn.rand(config=ref, s=(-1, 1, 1, -1), D=(2, 3, 4, 5))
+        b = yastn.rand(config=ref, s=(1, -1, 1), D=(2, 3, 5), dtype="complex128")
+        pairs = [(((0, 3), (0, 2)), (0, 0)), (((), ()), (0, 0))]
+    elif sym == "Z2":
+        L = yastn.Leg(ref, s=1, t=(0, 1), D=(7, 9)); p = yastn.Leg(ref, s=1, t=(0, 1), D=(1, 1))
+        a = yastn.rand(ref, legs=[L.conj(), p, p, L], n=0)
+        b = yastn.rand(ref, legs=[L.conj(), p, L], n=1)
+        pairs = [((3, 0), (0, 0)), (((0, 1), (0, 1)), (0, 1))]
+    elif sym == "U1xU1":
+        L = yastn.gaussian_leg(ref, s=1, n=(0, 0), sigma=1.0, D_total=24, method="round")
+        p = yastn.Leg(ref, s=1, t=((0, 0), (1, 0), (0, 1), (1, 1)), D=(1, 1, 1, 1))
+        a = yastn.rand(ref, legs=[L.conj(), p, L], n=(0, 0), dtype="complex128")
+        b = yastn.rand(ref, legs=[L.conj(), p.conj(), p, L], n=(0, 0), dtype="complex128")
+        pairs = [((2, 0), (0, 0)), (((1, 2), (1, 0)), (0, 0))]
+    else:
+        t1 = ((0, -1), (0, 1), (1, -1), (1, 1))
+        a = yastn.rand(config=ref, s=(-1, 1, 1, -1), t=(t1, t1, t1, t1), D=((1, 2, 2, 4), (9, 4, 3, 2), (5, 6, 7, 8), (7, 8, 9, 10)))
+        b = yastn.rand(config=ref, s=(1, -1, 1), t=(t1, t1, t1), D=((1, 2, 2, 4), (9, 4, 3, 2), (4, 5, 6, 3)))
+        pairs = [(((0, 1), (0, 1)), (0, 0)), ((0, 0), (0, 0))]
+    A, B = mirror(a, our), mirror(b, our)
+    for axes, conj in pairs:
+        close(yastn.tensordot(A, B, axes=axes, conj=conj), yastn.tensordot(a, b, axes=axes, conj=conj))
+
+
+@pytest.mark.parametrize("policy", POLICIES)
+def test_missing_charges_and_empty_result(device, policy):
+    """Blocks without a partner are filtered (_common_inds), merges pad with zeros, empty result has size 0
+    (reference: tests/tensor/test_tensordot.py:140-170)."""
+    ref, our = cfgs("U1", policy, device)
+    ref.backend.random_seed(7)
+    a = yastn.rand(config=ref, s=(-1, 1, 1), t=((-2, 0, 2), (-1, 1), (-3, -1, 1, 3)), D=((2, 3, 4), (5, 6), (1, 2, 3, 4)))
+    b = yastn.rand(config=ref, s=(-1, 1, 1), t=((-3, -1, 5), (0, 1), (-1, 0, 1)), D=((1, 2, 7), (3, 2), (2, 3, 4)))
+    A, B = mirror(a, our), mirror(b, our)
+    close(yastn.tensordot(A, B, axes=(2, 0)), yastn.tensordot(a, b, axes=(2, 0)))
+    close(yastn.tensordot(B, A, axes=(0, 2)), yastn.tensordot(b, a, axes=(0, 2)))
+    a3 = yastn.rand(config=ref, s=(-1, 1), t=((0,), (0,)), D=((2,), (3,)))
+    b3 = yastn.rand(config=ref, s=(-1, 1), t=((1,), (1,)), D=((4,), (5,)))
+    c = yastn.tensordot(mirror(a3, our), mirror(b3, our), axes=(1, 0))
+    r = yastn.tensordot(a3, b3, axes=(1, 0))
+    same_structure(c, r)
+    assert c.size == 0
+
+
+def test_fuse_unfuse_transpose(device):
+    """fuse_legs(mode='hard') = transpose_and_merge with an N-d target, unfuse_legs = unmerge, consume_transpose =
+    transpose (reference: yastn/tensor/_merging.py:283-301,466-468, _single.py:316-346).  Pure data movement: exact."""
+    ref, our = cfgs("U1", "fuse_to_matrix", device)
+    ref.backend.random_seed(9)
+    a = yastn.rand(config=ref, s=(-1, 1, 1, -1, 1), t=((-1, 0, 1), (0, 1), (-1, 1), (0, 1, 2), (-1, 0)),
+                   D=((2, 3, 2), (3, 2), (2, 4), (1, 2, 3), (2, 2)), dtype="complex128")
+    A = mirror(a, our)
+    f, F = a.fuse_legs(axes=((0, 2), 1, (4, 3)), mode="hard"), A.fuse_legs(axes=((0, 2), 1, (4, 3)), mode="hard")
+    close(F, f, tol=0)
+    close(F.unfuse_legs(axes=(0, 2)), f.unfuse_legs(axes=(0, 2)), tol=0)
+    f2, F2 = f.fuse_legs(axes=((0, 1), 2), mode="hard"), F.fuse_legs(axes=((0, 1), 2), mode="hard")
+    close(F2, f2, tol=0)
+    close(F2.unfuse_legs(axes=0).unfuse_legs(axes=(0, 2)), f2.unfuse_legs(axes=0).unfuse_legs(axes=(0, 2)), tol=0)
+    close(A.transpose((4, 2, 0, 3, 1)).consume_transpose(), a.transpose((4, 2, 0, 3, 1)).consume_transpose(), tol=0)
+    close(A.conj().transpose((1, 0, 2, 4, 3)).consume_transpose(), a.conj().transpose((1, 0, 2, 4, 3)).consume_transpose(), tol=0)
+    # hard-fused operands contracted over the fused leg
+    b = yastn.rand(config=ref, s=(1, -1, -1), t=((-1, 0, 1), (-1, 1), (0, 1)), D=((2, 3, 2), (2, 4), (3, 2)))
+    B = mirror(b, our)
+    close(yastn.tensordot(F, B.fuse_legs(axes=((0, 1), 2), mode="hard"), axes=(0, 0)),
+          yastn.tensordot(f, b.fuse_legs(axes=((0, 1), 2), mode="hard"), axes=(0, 0)))
+
+
+@pytest.mark.parametrize("policy", POLICIES)
+def test_ncon_and_einsum(device, policy):
+    ref, our = cfgs("U1", policy, device)
+    ref.backend.random_seed(11)
+    a, b = u1_operands(ref, "float64")
+    A, B = mirror(a, our), mirror(b, our)
+    r = yastn.ncon([a, b, b], [[1, 2, -0, -1], [1, 2, 3], [-2, -3, 3]], conjs=(0, 0, 1))
+    c = yastn.ncon([A, B, B], [[1, 2, -0, -1], [1, 2, 3], [-2, -3, 3]], conjs=(0, 0, 1))
+    close(c, r)
+    r = yastn.einsum("abcd,abe->ecd", a, b)
+    c = yastn.einsum("abcd,abe->ecd", A, B)
+    close(c, r)
+    close(B.transpose((1, 2, 0)) @ A, b.transpose((1, 2, 0)) @ a)     # __matmul__ = tensordot(axes=(ndim-1, 0))
+
+
+@pytest.mark.parametrize("policy", POLICIES)
+def test_autograd_through_tensordot(device, policy):
+    """Gradients of |tensordot|^2 against the stock torch backend (reference: tests/tensor/test_tensordot_ad.py:32-60)."""
+    stock = yastn.make_config(sym="U1", backend="torch", tensordot_policy=policy, default_dtype="float64")
+    _, our = cfgs("U1", policy, device)
+    stock.backend.random_seed(13)
+    a, b = u1_operands(stock, "complex128")
+    A, B = mirror(a, our), mirror(b, our)
+    grads = []
+    for x, y in ((a, b), (A, B)):
+        x.requires_grad_(True); y.requires_grad_(True)
+        c = yastn.tensordot(x, y, axes=((0, 1), (0, 1)))
+        loss = c.norm() ** 2
+        loss.backward()
+        grads.append((x._data.grad.detach().cpu().numpy(), y._data.grad.detach().cpu().numpy()))
+    for g_ref, g in zip(grads[0], grads[1]):
+        assert np.linalg.norm(g - g_ref) <= 1e-11 * np.linalg.norm(g_ref)
+
+
+def test_backend_module_contract(device):
+    import yastn.backend.backend_torch as stock
+    mod = yastn_backend.module()
+    assert mod is yastn_backend.module()                     # stable identity: _config is an lru key
+    assert mod.BACKEND_ID == "torch" and mod.DTYPE is stock.DTYPE
+    for name in stock.__all__:
+        assert hasattr(mod, name), name
+    hash(mod)
+    # tensors of the two backends are combinable (same BACKEND_ID), like the reference requires (_tests.py:38-39)
+    ref, our = cfgs("U1", "fuse_to_matrix", device)
+    if device == "cpu":
+        stock_cfg = yastn.make_config(sym="U1", backend="torch", tensordot_policy="fuse_to_matrix")
+        a, b = u1_operands(stock_cfg, "float64")
+        A = mirror(a, our)
+        close(yastn.tensordot(A, b, axes=((0, 1), (0, 1))), yastn.tensordot(a, b, axes=((0, 1), (0, 1))))
+
+
+def test_activate_rebinds_stock_backend(device):
+    import yastn.backend.backend_torch as stock
+    orig = stock.dot
+    try:
+        yastn_backend.activate()
+        assert stock.dot is not orig
+        cfg = yastn.make_config(sym="U1", backend="torch", default_device=device)
+        ref = yastn.make_config(sym="U1", backend="np")
+        ref.backend.random_seed(17)
+        a, b = u1_operands(ref, "float64")
+        n0 = yastn_backend.call_counts()["native"]["dot"]
+        close(yastn.tensordot(mirror(a, cfg), mirror(b, cfg), axes=((0, 1), (0, 1))), yastn.tensordot(a, b, axes=((0, 1), (0, 1))))
+        assert yastn_backend.call_counts()["native"]["dot"] == n0 + 1
+    finally:
+        yastn_backend.deactivate()
+    assert stock.dot is orig
+
+
+def test_cpu_tensor_is_rejected_without_shim():
+    cpu_shim.uninstall()
+    cfg = yastn.make_config(sym="U1", backend=yastn_backend.module(), default_device="cpu")
+    a, b = u1_operands(cfg, "float64")
+    with pytest.raises(TypeError, match="no CPU path"):
+        yastn.tensordot(a, b, axes=((0, 1), (0, 1)))
+
+
+def test_dmrg_heisenberg_small(device):
+    """Config 1 (reduced): U(1) Heisenberg chain 2-site DMRG runs unmodified on our backend and reproduces the
+    energy of the reference numpy backend (reference: tests/mps/test_dmrg.py, yastn/tn/mps/_dmrg.py:42-249)."""
+    import yastn.tn.mps as mps
+    energies = []
+    N, D = (8, 16)
+    for which in ("ref", "our"):
+        ref, our = cfgs("U1", "fuse_to_matrix", device)
+        cfg = ref if which == "ref" else our
+        ops = yastn.operators.Spin12(sym="U1", backend=cfg.backend, default_device=cfg.default_device, tensordot_policy="fuse_to_matrix")
+        ops.random_seed(seed=0)
+        I = mps.product_mpo(ops.I(), N)
+        terms = []
+        for n in range(N - 1):
+            terms.append(mps.Hterm(1.0, [n, n + 1], [ops.sz(), ops.sz()]))
+            terms.append(mps.Hterm(0.5, [n, n + 1], [ops.sp(), ops.sm()]))
+            terms.append(mps.Hterm(0.5, [n, n + 1], [ops.sm(), ops.sp()]))
+        H = mps.generate_mpo(I, terms)
+        psi = mps.random_mps(I, n=0, D_total=8)
+        out = mps.dmrg_(psi, H, method="2site", max_sweeps=6, opts_svd={"tol": 1e-10, "D_total": D}, energy_tol=1e-10)
+        energies.append(float(out.energy))
+    # N=8 open Heisenberg chain ground state energy (exact diagonalisation): -3.374932598687897
+    assert abs(energies[0] - (-3.374932598687897)) < 1e-7
+    assert abs(energies[1] - energies[0]) < 1e-8

@@ -14,8 +14,8 @@ function is differentiable (explicit backward, like the reference's autograd.Fun
 ONE kernel launch through the C ABI (include/yastn_b200.h) instead of a Python loop over blocks.
 Only CUDA float64 / complex128 tensors are accepted: there is no CPU or eager-torch fallback.
 
-Use with YASTN either as ``yastn.make_config(backend=yastn_b200.backend_b200.as_yastn_backend(), ...)`` or by
-``activate()`` which rebinds the five functions on ``yastn.backend.backend_torch``.
+Use with YASTN through ``yastn_b200.yastn_backend`` (``module()`` for ``yastn.make_config(backend=...)`` or
+``activate()`` which rebinds the five functions on ``yastn.backend.backend_torch``).
 """
 import ctypes
 
@@ -63,27 +63,26 @@ def _stream(dev):
     return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
+def _on_device(dev, launch):
+    """Run ``launch(stream)`` with ``dev`` current (plans and streams are per device)."""
+    if torch.cuda.current_device() != dev.index:
+        with torch.cuda.device(dev):
+            launch(_stream(dev))
+    else:
+        launch(_stream(dev))
+
+
 def _run_copy(plan, src, dst, zero):
     raw, conj = _raw(src)
     flags = (_lib.YB_COPY_ZERO_DST if zero else 0) | (_lib.YB_COPY_CONJ if conj else 0)
-    dev = src.device
-    if torch.cuda.current_device() != dev.index:
-        with torch.cuda.device(dev):
-            plan.run(raw.data_ptr(), dst.data_ptr(), dst.numel(), flags, _stream(dev))
-    else:
-        plan.run(raw.data_ptr(), dst.data_ptr(), dst.numel(), flags, _stream(dev))
+    _on_device(src.device, lambda st: plan.run(raw.data_ptr(), dst.data_ptr(), dst.numel(), flags, st))
 
 
 def _run_gemm(plan, A, B, C, conj_a=False, conj_b=False):
     ra, ca = _raw(A)
     rb, cb = _raw(B)
     flags = (_lib.YB_GEMM_CONJ_A if (ca != conj_a) else 0) | (_lib.YB_GEMM_CONJ_B if (cb != conj_b) else 0)
-    dev = C.device
-    if torch.cuda.current_device() != dev.index:
-        with torch.cuda.device(dev):
-            plan.run(ra.data_ptr(), rb.data_ptr(), C.data_ptr(), flags, _stream(dev))
-    else:
-        plan.run(ra.data_ptr(), rb.data_ptr(), C.data_ptr(), flags, _stream(dev))
+    _on_device(C.device, lambda st: plan.run(ra.data_ptr(), rb.data_ptr(), C.data_ptr(), flags, st))
 
 
 # -------------------------------------------------------------------------------------------------
