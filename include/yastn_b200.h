@@ -72,8 +72,18 @@ void yb_copy_plan_destroy(yb_copy_plan* plan);
  * ---------------------------------------------------------------------------------------------- */
 int yb_gemm_plan_create(const int64_t* problems, int64_t nprob, const int64_t* segments, int64_t nseg, int dtype,
                         int device, yb_gemm_plan** out);
-/* info[0]=tiles, [1]=real multiply-adds (M*N*K summed), [2]=64x128 tiles, [3]=64x64 tiles */
-int yb_gemm_plan_info(const yb_gemm_plan* plan, int64_t info[4]);
+/* Same, with a fused unmerge epilogue (backend.unmerge, _backend_torch_backwards.py:397-408, applied while the
+ * block is still in registers): problem p with scat_index[p] = s >= 0 does not store its M x N block row-major at
+ * offC; instead the block is cut by row_cuts[row_ptr[s] .. row_ptr[s+1]) (0 = c_0 < c_1 < .. < c_nrs = M) and
+ * col_cuts[col_ptr[s] .. col_ptr[s+1]) and sub-block (i, j) is written contiguously (row-major, its own width) at
+ * element offset dst[dst_ptr[s] + i*ncs + j] of C.  scat_index[p] = -1 keeps the plain store. */
+int yb_gemm_plan_create_scatter(const int64_t* problems, int64_t nprob, const int64_t* segments, int64_t nseg,
+                                const int64_t* scat_index, int64_t nscat, const int64_t* row_ptr, const int64_t* row_cuts,
+                                const int64_t* col_ptr, const int64_t* col_cuts, const int64_t* dst_ptr, const int64_t* dst,
+                                int dtype, int device, yb_gemm_plan** out);
+/* info[0]=tiles, [1]=real multiply-adds (M*N*K summed), [2]=big tiles, [3]=small tiles, [4]=grid (CTAs), [5]=CTAs that
+ * start inside a tile (stream-K partials).  Plans of one device share a stream-K workspace: run them on one stream at a time. */
+int yb_gemm_plan_info(const yb_gemm_plan* plan, int64_t info[6]);
 int yb_gemm_run(const yb_gemm_plan* plan, const void* A, const void* B, void* C, int flags, void* stream);
 void yb_gemm_plan_destroy(yb_gemm_plan* plan);
 

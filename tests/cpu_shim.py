@@ -45,7 +45,8 @@ class CpuCopyPlan:
 
 
 class CpuGemmPlan:
-    def __init__(self, problems, segments, dtype_code, device):
+    def __init__(self, problems, segments, dtype_code, device, scatter=None):
+        self.scatter = None if scatter is None else [np.ascontiguousarray(t, dtype=np.int64) for t in scatter]
         self.problems = np.ascontiguousarray(problems, dtype=np.int64)
         self.segments = np.ascontiguousarray(segments, dtype=np.int64)
         self.itemsize = 16 if dtype_code == _lib.YB_C128 else 8
@@ -59,11 +60,17 @@ class CpuGemmPlan:
                     continue
                 na = max(na, offA + (M - 1) * sAm + (K - 1) * sAk + 1)
                 nb = max(nb, offB + (K - 1) * sBk + (N - 1) * sBn + 1)
+        if self.scatter is not None:
+            _, row_ptr, row_cuts, col_ptr, col_cuts, dst_ptr, dst = self.scatter
+            for s in range(len(row_ptr) - 1):
+                rc, cc = row_cuts[row_ptr[s]:row_ptr[s + 1]], col_cuts[col_ptr[s]:col_ptr[s + 1]]
+                d = dst[dst_ptr[s]:dst_ptr[s + 1]].reshape(len(rc) - 1, len(cc) - 1)
+                nc = max(nc, int((d + np.diff(rc)[:, None] * np.diff(cc)[None, :]).max()))
         self.na, self.nb, self.nc = int(na), int(nb), int(nc)
 
     def run(self, a_ptr, b_ptr, c_ptr, flags, stream):
         A, B, C = _view(a_ptr, self.na, self.itemsize), _view(b_ptr, self.nb, self.itemsize), _view(c_ptr, self.nc, self.itemsize)
-        exec_gemm(self.problems, self.segments, A, B, C, bool(flags & _lib.YB_GEMM_CONJ_A), bool(flags & _lib.YB_GEMM_CONJ_B))
+        exec_gemm(self.problems, self.segments, A, B, C, bool(flags & _lib.YB_GEMM_CONJ_A), bool(flags & _lib.YB_GEMM_CONJ_B), self.scatter)
 
 
 _saved = {}

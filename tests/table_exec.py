@@ -18,8 +18,8 @@ def exec_copy(recs, rank, src, dst):
     return dst
 
 
-def exec_gemm(problems, segments, A, B, C, conj_a=False, conj_b=False):
-    for (M, N, offC, ldc, s0, s1) in problems:
+def exec_gemm(problems, segments, A, B, C, conj_a=False, conj_b=False, scatter=None):
+    for p, (M, N, offC, ldc, s0, s1) in enumerate(problems):
         acc = np.zeros((M, N), dtype=C.dtype)
         m = np.arange(M)[:, None]
         n = np.arange(N)[None, :]
@@ -32,5 +32,16 @@ def exec_gemm(problems, segments, A, B, C, conj_a=False, conj_b=False):
             if conj_b:
                 b = b.conj()
             acc += a @ b
-        C[offC + m * ldc + n] = acc
+        if scatter is not None and scatter[0][p] >= 0:
+            scat_index, row_ptr, row_cuts, col_ptr, col_cuts, dst_ptr, dst = scatter
+            s = scat_index[p]
+            rc = row_cuts[row_ptr[s]:row_ptr[s + 1]]
+            cc = col_cuts[col_ptr[s]:col_ptr[s + 1]]
+            d = dst[dst_ptr[s]:dst_ptr[s + 1]].reshape(len(rc) - 1, len(cc) - 1)
+            for i in range(len(rc) - 1):
+                for j in range(len(cc) - 1):
+                    blk = acc[rc[i]:rc[i + 1], cc[j]:cc[j + 1]]
+                    C[d[i, j]:d[i, j] + blk.size] = blk.reshape(-1)
+        else:
+            C[offC + m * ldc + n] = acc
     return C

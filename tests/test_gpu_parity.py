@@ -240,3 +240,70 @@ def test_empty_and_degenerate(bk):
     a = np.arange(1, 6, dtype=np.float64); b = np.arange(1, 8, dtype=np.float64)
     out = bk.dot(_dev(a), _dev(b), (((0, 35), (5, 7), (0, 5), (5, 1), (0, 7), (1, 7)),), 35)
     assert np.array_equal(out.cpu().numpy(), np.outer(a, b).reshape(-1))
+
+
+@pytest.mark.parametrize("name", ["U1_D64_P1", "U1_D1024_P1", "U1_D1024_P3", "Z2_D512_P1", "U1xU1_D4096_P1", "U1_D4096_P1"])
+@pytest.mark.parametrize("dtype", ["float64", "complex128"])
+def test_fused_dot_unmerge_matches_two_calls(bk, name, dtype):
+    """The scatter epilogue (dot + unmerge in one launch) gives bit-identical data to dot followed by unmerge."""
+    case = bench_structs()[name]
+    st = case["f2m"]
+    rng = np.random.default_rng(12)
+    md, um = st["dot"]["meta_dot"], st["unmerge"]["meta"]
+    na = max(r[2][1] for r in md); nb = max(r[4][1] for r in md)
+    A = rng.uniform(-1, 1, na); B = rng.uniform(-1, 1, nb)
+    if dtype == "complex128":
+        A = A + 1j * rng.uniform(-1, 1, na); B = B + 1j * rng.uniform(-1, 1, nb)
+    A, B = _dev(A), _dev(B)
+    two = bk.unmerge(bk.dot(A, B, md, st["dot"]["Dsize"]), um)
+    one = bk.dot_unmerge(A, B, md, st["dot"]["Dsize"], um)
+    torch.cuda.synchronize()
+    assert torch.equal(one, two)
+    # backward of the fused call = backward of the two calls
+    A1, B1 = A.clone().requires_grad_(True), B.clone().requires_grad_(True)
+    A2, B2 = A.clone().requires_grad_(True), B.clone().requires_grad_(True)
+    G = torch.randn_like(two)
+    bk.dot_unmerge(A1, B1, md, st["dot"]["Dsize"], um).backward(G)
+    bk.unmerge(bk.dot(A2, B2, md, st["dot"]["Dsize"]), um).backward(G)
+    assert torch.equal(A1.grad, A2.grad) and torch.equal(B1.grad, B2.grad)
+
+
+def test_stream_k_is_deterministic_and_splits(bk):
+    """Huge-K / tiny-output contraction (pattern P3): the k-range of a tile is shared by many CTAs (stream-K); partials are
+    added in fixed CTA order, so repeated runs are bit-identical, and the result matches a per-sector torch.matmul."""
+    from yastn_b200 import plans as _plans
+    case = bench_structs()["U1_D2048_P3"]
+    st = case["f2m"]
+    md = st["dot"]["meta_dot"]
+    problems, segments = _plans.dot_tables(md)
+    info = _plans.GemmPlan(problems, segments, 0, torch.cuda.current_device()).info()
+    assert info["split_ctas"] > 100 and info["grid"] > 100      # 3 tiny output blocks spread over the whole GPU
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    na = max(r[2][1] for r in md); nb = max(r[4][1] for r in md)
+    A = torch.rand(na, dtype=torch.float64, device="cuda", generator=gen) * 2 - 1
+    B = torch.rand(nb, dtype=torch.float64, device="cuda", generator=gen) * 2 - 1
+    C1 = bk.dot(A, B, md, st["dot"]["Dsize"])
+    for _ in range(3):
+        assert torch.equal(bk.dot(A, B, md, st["dot"]["Dsize"]), C1)
+    for slc, Dc, sla, Da, slb, Db in md:
+        ref = A[sla[0]:sla[1]].view(Da) @ B[slb[0]:slb[1]].view(Db)
+        got = C1[slc[0]:slc[1]].view(Dc)
+        assert float(torch.linalg.norm(got - ref) / torch.linalg.norm(ref)) <= 1e-12
+
+
+def test_gemm_unaligned_operands_and_ragged_shapes(bk):
+    """Odd offsets / odd leading dimensions (8-byte aligned only), shapes that are not multiples of any tile, K = 1 .. 50."""
+    rng = np.random.default_rng(21)
+    recs, oa, ob, oc = [], 1, 3, 5
+    for (M, K, N) in [(1, 1, 1), (3, 5, 7), (65, 17, 129), (64, 16, 128), (63, 15, 127), (130, 33, 67), (7, 50, 300), (257, 1, 9), (33, 47, 1)]:
+        recs.append(((oc, oc + M * N), (M, N), (oa, oa + M * K), (M, K), (ob, ob + K * N), (K, N)))
+        oa += M * K + 1; ob += K * N + 1; oc += M * N
+    for dtype in ("float64", "complex128"):
+        A = rng.standard_normal(oa); B = rng.standard_normal(ob)
+        if dtype == "complex128":
+            A = A + 1j * rng.standard_normal(oa); B = B + 1j * rng.standard_normal(ob)
+        meta = tuple(recs)
+        ref = orc.dot(A, B, meta, oc)
+        out = bk.dot(_dev(A), _dev(B), meta, oc).cpu().numpy()
+        for slc, *_ in recs:
+            assert _relerr(out[slc[0]:slc[1]], ref[slc[0]:slc[1]]) <= TOL

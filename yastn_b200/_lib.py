@@ -20,6 +20,8 @@ SIGNATURES = {
     "yb_copy_run": (_c.c_int, [_vp, _vp, _vp, _c.c_int64, _c.c_int, _vp]),
     "yb_copy_plan_destroy": (None, [_vp]),
     "yb_gemm_plan_create": (_c.c_int, [_vp, _c.c_int64, _vp, _c.c_int64, _c.c_int, _c.c_int, _c.POINTER(_vp)]),
+    "yb_gemm_plan_create_scatter": (_c.c_int, [_vp, _c.c_int64, _vp, _c.c_int64, _vp, _c.c_int64, _vp, _vp, _vp, _vp, _vp, _vp,
+                                               _c.c_int, _c.c_int, _c.POINTER(_vp)]),
     "yb_gemm_plan_info": (_c.c_int, [_vp, _i64p]),
     "yb_gemm_run": (_c.c_int, [_vp, _vp, _vp, _vp, _c.c_int, _vp]),
     "yb_gemm_plan_destroy": (None, [_vp]),

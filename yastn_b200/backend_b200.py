@@ -254,6 +254,43 @@ class _Dot(torch.autograd.Function):
         return gA, gB, None, None
 
 
+class _DotUnmerge(torch.autograd.Function):
+    """dot followed by unmerge in ONE launch: the GEMM epilogue scatters straight into the unmerged block layout
+    (reference: the two calls at yastn/tensor/_contractions.py:152-155).  Backward = adjoint unmerge + dot backward."""
+
+    @staticmethod
+    def forward(Adata, Bdata, meta_dot, Dsize, meta_unmerge):
+        Adata, Bdata, dtype = _promote(Adata, Bdata)
+        dev = Adata.device.index
+        key = ("dotunm", id(meta_dot), id(meta_unmerge), dtype, dev)
+
+        def build():
+            problems, segments = plans.dot_tables(meta_dot)
+            scatter = plans.unmerge_scatter_tables(meta_dot, meta_unmerge)
+            return {"fwd": plans.GemmPlan(problems, segments, _DTYPE_CODE[dtype], dev, scatter), "ref": meta_unmerge}
+        ent = _CACHE.get(key, meta_dot, build)
+        out = torch.empty(Dsize, dtype=dtype, device=Adata.device)
+        _run_gemm(ent["fwd"], Adata, Bdata, out)
+        return out
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        Adata, Bdata, meta_dot, Dsize, meta_unmerge = inputs
+        ctx.save_for_backward(Adata, Bdata)
+        ctx.metas = (meta_dot, Dsize, meta_unmerge)
+
+    @staticmethod
+    def backward(ctx, grad):
+        meta_dot, Dsize, meta_unmerge = ctx.metas
+        Adata, Bdata = ctx.saved_tensors
+        with torch.enable_grad():
+            A = Adata.detach().requires_grad_(True)
+            B = Bdata.detach().requires_grad_(True)
+            out = _Unmerge.apply(_Dot.apply(A, B, meta_dot, Dsize), meta_unmerge)
+        gA, gB = torch.autograd.grad(out, (A, B), grad)
+        return gA, gB, None, None, None
+
+
 def _tds_plans(meta_dot, Areshape, Breshape, Aorder, Border, dtype, device):
     key = ("tds", id(meta_dot), id(Areshape), id(Breshape), tuple(Aorder), tuple(Border), dtype, device)
 
@@ -367,6 +404,13 @@ def dot(Adata, Bdata, meta_dot, Dsize):
     _check(Adata, "dot")
     _check(Bdata, "dot")
     return _Dot.apply(Adata, Bdata, meta_dot, Dsize)
+
+
+def dot_unmerge(Adata, Bdata, meta_dot, Dsize, meta_unmerge):
+    """``unmerge(dot(Adata, Bdata, meta_dot, Dsize), meta_unmerge)`` in one launch (fused scatter epilogue)."""
+    _check(Adata, "dot_unmerge")
+    _check(Bdata, "dot_unmerge")
+    return _DotUnmerge.apply(Adata, Bdata, meta_dot, Dsize, meta_unmerge)
 
 
 def transpose_dot_sum(Adata, Bdata, meta_dot, Areshape, Breshape, Aorder, Border, Dsize):

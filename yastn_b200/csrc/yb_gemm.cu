@@ -1,14 +1,21 @@
 // Grouped variable-shape block GEMM on the FP64 tensor pipe (DMMA.8x8x4) for float64 and complex128.
 //
 // Replaces the per-sector loop of backend.dot (yastn/backend/_backend_torch_backwards.py:100-109: one cuBLAS
-// launch + one slice copy per charge sector) and the per-pair loop of backend.transpose_dot_sum (:143-157)
-// by ONE launch over all sectors.  FP64 has no tcgen05/TMEM path on sm_100a (tcgen05.mma kinds are
-// f16/tf32/f8f6f4/i8/mx*); the FP64 tensor instruction is the warp-level DMMA.8x8x4 (every wider
-// mma.sync f64 shape lowers to it), measured at 37.1 TFLOP/s on B200 (tools/microbench/fp64_pipes.cu),
-// and operands are only 8-byte aligned in general, which rules out TMA tensor maps (16-byte base/stride).
-// The kernel therefore uses a multi-stage cp.async pipeline into XOR-swizzled shared memory and
-// register-blocked DMMA, one CTA per output tile, tiles ordered longest-first so the hardware block
-// scheduler does the load balancing across all problems of the group.
+// launch + one slice copy per charge sector), the per-pair loop of backend.transpose_dot_sum (:143-157) and —
+// through the scatter epilogue — the per-block loop of backend.unmerge (:397-408) by ONE persistent launch.
+//
+// FP64 has no tcgen05/TMEM path on sm_100a (tcgen05.mma kinds are f16/tf32/f8f6f4/i8/mx*); the FP64 tensor
+// instruction is the warp-level DMMA.8x8x4 (every wider mma.sync f64 shape lowers to it), measured at
+// 37.1 TFLOP/s on B200 (tools/microbench/fp64_pipes.cu).  Block offsets and leading dimensions of YASTN's 1-D
+// storage are arbitrary element counts, i.e. float64 operands are only 8-byte aligned in general, which rules
+// out TMA (16-byte global alignment); tiles are staged with a multi-stage cp.async pipeline into XOR-swizzled
+// shared memory (16-byte copies when a sector happens to be aligned, 8-byte copies otherwise).
+//
+// Scheduling is stream-K: the k-iterations of all output tiles of all sectors form one weighted work line that
+// the host cuts into equal shares, one per resident CTA (grid = SMs x occupancy).  A CTA that starts in the
+// middle of a tile writes its partial accumulators to a per-CTA workspace slot and raises a flag; the CTA that
+// started the tile adds the partials in fixed CTA order (deterministic) and runs the epilogue.  This keeps
+// every SM busy for few large sectors, many tiny sectors and the huge-K / tiny-output shape alike.
 //
 // complex128 uses the 4M scheme on the same pipe: Cr += Ar*Br - Ai*Bi ; Ci += Ar*Bi + Ai*Br, with
 // conjugation of either operand folded into the fragment loads (torch's lazy conj bit).
@@ -19,13 +26,16 @@
 namespace yb {
 
 constexpr int kGemmThreads = 128;   // 2 x 2 warps
-constexpr int kStages = 3;
+constexpr int kStages = 4;
 constexpr int kRowBytes = 128;      // bytes of one K-row (KC format): 16 doubles or 8 complex
+constexpr int kWsDoubles = 64 * kGemmThreads;   // partial-accumulator slot per CTA (64 doubles per thread)
 
 struct GemmProblem {
     int32_t M, N;
     int32_t seg_begin, seg_end;
     int64_t offC, ldc;
+    int32_t scat;      // index into the scatter table, -1: plain row-major store at offC / ldc
+    int32_t pad_;
 };
 
 struct GemmSegment {
@@ -36,7 +46,41 @@ struct GemmSegment {
 };
 
 struct GemmTile {
-    int32_t prob, m0, n0, cfg;  // cfg 0: 64x128, 1: 64x64
+    int32_t prob, m0, n0, cfg;   // cfg 0: big tile, 1: small tile
+    int32_t iters;               // k-iterations of the whole tile (sum over segments of ceil(K / BK))
+    int32_t pad_[3];
+};
+
+// Share of one CTA: tiles [tile_begin, tile_end], starting at k-iteration it_begin of the first tile and ending
+// before k-iteration it_end of the last one.
+struct CtaRange {
+    int32_t tile_begin, it_begin, tile_end, it_end;
+};
+
+// Fused unmerge: element (r, c) of the merged block goes to  dst[rowinfo[r].x * ncs + colinfo[c].x]
+//                                                            + rowinfo[r].y * colinfo[c].z + colinfo[c].y
+struct ScatterInfo {
+    int64_t dst_off;             // into the int64 pool of destination block offsets (nrs x ncs)
+    int32_t row_off, col_off;    // into the int2 (row) / int4 (col) pools
+    int32_t ncs, pad_;
+};
+
+struct GemmArgs {
+    const GemmProblem* problems;
+    const GemmSegment* segs;
+    const GemmTile* tiles;
+    const CtaRange* ranges;
+    const ScatterInfo* scat;
+    const int2* rowinfo;
+    const int4* colinfo;
+    const int64_t* dstpool;
+    double* ws;
+    int* sync_flags;
+    const char* A;
+    const char* B;
+    char* C;
+    int flags;
+    int base_aligned;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -71,6 +115,14 @@ __device__ __forceinline__ double2 lds128(uint32_t saddr) {
     asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "r"(saddr));
     return v;
 }
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
 
 // Shared-memory operand tile formats.  x is the non-contracted index (m for A, n for B).
 //   KC: [x][kRowBytes]  — K contiguous (row-major A, or B^T/B^H);   chunk swizzle by x
@@ -84,51 +136,86 @@ struct ElemTraits {
     static constexpr int KSTEPS = BK / 4;               // DMMA k-steps per stage
 };
 
-// Loader of one operand tile (BX non-contracted x BK contracted) for stage `sbase`.
-// All 128 threads cooperate; 16-byte chunks, zero-filled outside the problem.
+// Loader of one operand tile (BX non-contracted x BK contracted).  All 128 threads cooperate, 16-byte chunks,
+// zero-filled outside the problem.  Thread t owns chunks t, t+128, ...: they share the coordinate along the
+// contiguous dim and are RSTEP apart along the strided one, so the global address of chunk i is
+// g0 + i * cstep and a k-iteration only advances g0 — no per-chunk index arithmetic in the main loop.
 template <bool CPLX, int LAYOUT, int BX>
 struct TileLoader {
     using TR = ElemTraits<CPLX>;
     static constexpr int ES = TR::ES, BK = TR::BK;
     static constexpr int CHUNKS = BX * BK * ES / 16;            // 16B chunks per tile
-    static constexpr int PER_THREAD = CHUNKS / kGemmThreads;
+    static constexpr int NCH = CHUNKS / kGemmThreads;           // chunks per thread
     static constexpr int CPR = (LAYOUT == KC) ? (kRowBytes / 16) : (BX * ES / 16);  // chunks per smem row
     static constexpr int EPC = 16 / ES;                          // elements per chunk
+    static constexpr int RSTEP = kGemmThreads / CPR;             // smem rows between consecutive chunks of a thread
+    static constexpr int ROWB = (LAYOUT == KC) ? kRowBytes : BX * ES;   // bytes of one smem row
+    static_assert(CPR <= kGemmThreads && kGemmThreads % CPR == 0 && NCH >= 1, "tile / thread mismatch");
+    static_assert(LAYOUT == KC || RSTEP % 2 == 0, "XC swizzle update assumes an even row step");
 
-    // ptr: operand base (already offset by the segment's off); sx / sk: strides of x and k; X,K: extents;
-    // x0,k0: tile origin.  aligned16: every chunk start is 16B-aligned in global memory.
-    __device__ __forceinline__ static void load(uint32_t sbase, const char* ptr, int64_t sx, int64_t sk, int X, int K,
-                                                int x0, int k0, bool aligned16, int tid) {
+    const char* g0;     // global address of chunk 0 at the current k-iteration
+    uint32_t cstep;     // bytes between consecutive chunks of this thread
+    int64_t kadv;       // bytes per k-iteration
+    uint32_t soff0;     // smem offset of chunk 0 inside a stage
+    int lim;            // KC: bit mask of chunks whose row is inside the problem; XC: bytes (0..16) of every chunk
+    int c0;             // KC: first contracted index of this thread's chunks (j * EPC); XC: strided row r0
+    bool al16;
+
+    // base: operand base already offset to the segment; (sx, sk): strides of x and k; X: extent of x;
+    // x0: tile origin; k0: first contracted index of the first iteration
+    __device__ __forceinline__ void init(const char* base, int64_t sx, int64_t sk, int X, int x0, int k0, bool aligned16, int tid) {
+        const int r0 = tid / CPR, j = tid % CPR;
+        al16 = CPLX || aligned16;
+        if (LAYOUT == KC) {
+            const int jj = CPLX ? (j ^ ((r0 & 1) << 2)) : (j ^ ((r0 & 3) << 1));
+            soff0 = r0 * ROWB + jj * 16;
+            g0 = base + ((int64_t)(x0 + r0) * sx + (int64_t)(k0 + j * EPC) * sk) * ES;
+            cstep = (uint32_t)(RSTEP * sx * ES);
+            kadv = (int64_t)BK * sk * ES;
+            lim = 0;
 #pragma unroll
-        for (int i = 0; i < PER_THREAD; ++i) {
-            const int idx = tid + i * kGemmThreads;
-            const int row = idx / CPR, j = idx % CPR;
-            int x, k, rem;       // element coordinates of the chunk start, elements remaining along the contiguous dim
-            uint32_t soff;
+            for (int i = 0; i < NCH; ++i) lim |= (x0 + r0 + i * RSTEP < X) ? (1 << i) : 0;
+            c0 = j * EPC;
+        } else {
+            const int jj = j ^ ((r0 & 3) << 1);
+            soff0 = r0 * ROWB + jj * 16;
+            g0 = base + ((int64_t)(x0 + j * EPC) * sx + (int64_t)(k0 + r0) * sk) * ES;
+            cstep = (uint32_t)(RSTEP * sk * ES);
+            kadv = (int64_t)BK * sk * ES;
+            int rem = (X - (x0 + j * EPC)) * ES;
+            lim = rem < 0 ? 0 : (rem > 16 ? 16 : rem);
+            c0 = r0;
+        }
+    }
+
+    // kleft = K - k0 of this iteration (>= 1)
+    __device__ __forceinline__ void issue(uint32_t sbase, int kleft) {
+        int cb = 16;
+        if (LAYOUT == KC) {
+            cb = (kleft - c0) * ES;
+            cb = cb < 0 ? 0 : (cb > 16 ? 16 : cb);
+        }
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+            int bytes;
+            uint32_t so;
             if (LAYOUT == KC) {
-                x = x0 + row;
-                k = k0 + j * EPC;
-                rem = (x < X) ? (K - k) : 0;
-                const int jj = CPLX ? (j ^ ((row & 1) << 2)) : (j ^ ((row & 3) << 1));
-                soff = row * kRowBytes + jj * 16;
+                bytes = ((lim >> i) & 1) ? cb : 0;
+                so = soff0 + i * RSTEP * ROWB;
             } else {
-                k = k0 + row;
-                x = x0 + j * EPC;
-                rem = (k < K) ? (X - x) : 0;
-                const int jj = j ^ ((row & 3) << 1);
-                soff = row * (BX * ES) + jj * 16;
+                bytes = (c0 + i * RSTEP < kleft) ? lim : 0;
+                // the swizzle term ((row & 3) << 1) changes with i when RSTEP is not a multiple of 4
+                so = (soff0 ^ ((((i * RSTEP) & 3) << 1) * 16)) + i * RSTEP * ROWB;
             }
-            rem = rem < 0 ? 0 : rem;
-            const char* g = ptr + ((int64_t)x * sx + (int64_t)k * sk) * ES;
-            if (rem == 0) g = ptr;  // keep the address valid; nothing is read
-            if (CPLX || aligned16) {
-                const int bytes = rem >= EPC ? 16 : rem * ES;
-                cp_async16(sbase + soff, g, bytes);
+            const char* g = g0 + (uint64_t)i * cstep;
+            if (al16) {
+                cp_async16(sbase + so, g, bytes);
             } else {
-                cp_async8(sbase + soff, g, rem >= 1 ? 8 : 0);
-                cp_async8(sbase + soff + 8, rem >= 2 ? g + 8 : ptr, rem >= 2 ? 8 : 0);
+                cp_async8(sbase + so, g, bytes >= 8 ? 8 : 0);
+                cp_async8(sbase + so + 8, g + 8, bytes >= 16 ? 8 : 0);
             }
         }
+        g0 += kadv;
     }
 };
 
@@ -155,18 +242,48 @@ struct TileKernel {
     static constexpr int ES = TR::ES, BK = TR::BK, KSTEPS = TR::KSTEPS;
     static constexpr int WM = BM / 2, WN = BN / 2;     // warp tile
     static constexpr int MT = WM / 8, NT = WN / 8;     // 8x8 DMMA tiles per warp
+    static constexpr int NACC = MT * NT * (CPLX ? 4 : 2);
     static constexpr int A_BYTES = BM * kRowBytes, B_BYTES = BN * kRowBytes;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int SMEM_BYTES = STAGE_BYTES * kStages;
+    static_assert(NACC <= 64, "workspace slot too small");
 
-    __device__ static void run(const GemmProblem& P, const GemmSegment* __restrict__ segs, const GemmTile& T,
-                               const char* __restrict__ A, const char* __restrict__ B, char* __restrict__ C,
-                               int flags, bool base_aligned, uint32_t smem) {
+    // Store one (row, col) / (row, col+1) accumulator pair.
+    template <typename T>
+    __device__ __forceinline__ static void store_pair(const GemmArgs& g, const GemmProblem& P, const ScatterInfo* S, T* Cbase,
+                                                      int row, int col, T v0, T v1, bool vec_ok) {
+        if (S == nullptr) {
+            T* p = Cbase + (int64_t)row * P.ldc + col;
+            if (!CPLX && vec_ok && col + 1 < P.N) {
+                *reinterpret_cast<double2*>(p) = make_double2(*reinterpret_cast<double*>(&v0), *reinterpret_cast<double*>(&v1));
+            } else {
+                if (col < P.N) p[0] = v0;
+                if (col + 1 < P.N) p[1] = v1;
+            }
+        } else {
+            const int2 ri = g.rowinfo[S->row_off + row];
+            const int64_t* dst = g.dstpool + S->dst_off + (int64_t)ri.x * S->ncs;
+            T* out = reinterpret_cast<T*>(g.C);
+            if (col < P.N) {
+                const int4 ci = g.colinfo[S->col_off + col];
+                out[dst[ci.x] + (int64_t)ri.y * ci.z + ci.y] = v0;
+            }
+            if (col + 1 < P.N) {
+                const int4 ci = g.colinfo[S->col_off + col + 1];
+                out[dst[ci.x] + (int64_t)ri.y * ci.z + ci.y] = v1;
+            }
+        }
+    }
+
+    // Run k-iterations [it_begin, it_end) of tile T; handles the stream-K fix-up and the epilogue.
+    __device__ static void run(const GemmArgs& g, const GemmProblem& P, const GemmTile& T, int tile_index, int it_begin, int it_end,
+                               uint32_t smem) {
+        const GemmSegment* __restrict__ segs = g.segs;
         const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
         const int wm0 = (warp >> 1) * WM, wn0 = (warp & 1) * WN;
         const int lx = lane >> 2, lk = lane & 3;
+        const bool base_aligned = g.base_aligned != 0;
 
-        // accumulators: real part (and imaginary part for complex)
         double acc[MT][NT][CPLX ? 4 : 2];
 #pragma unroll
         for (int i = 0; i < MT; ++i)
@@ -175,24 +292,45 @@ struct TileKernel {
 #pragma unroll
                 for (int c = 0; c < (CPLX ? 4 : 2); ++c) acc[i][j][c] = 0.0;
 
-        // iteration space: all K-chunks of all segments of this problem
-        int total_iters = 0;
-        for (int s = P.seg_begin; s < P.seg_end; ++s) total_iters += (segs[s].K + BK - 1) / BK;
+        const int n_iters = min(it_end, T.iters) - it_begin;   // T.iters may be 0 (all K == 0): plain zero block
 
-        // loader state
-        int ld_seg = P.seg_begin, ld_k0 = 0, ld_it = 0;
-        auto issue_load = [&](int stage) {
-            if (ld_it < total_iters) {
-                while (segs[ld_seg].K <= ld_k0) {  // also skips K == 0 segments
-                    ++ld_seg;
-                    ld_k0 = 0;
+        // loader state: position (segment, k0) of the next iteration to issue
+        TileLoader<CPLX, AL, BM> la;
+        TileLoader<CPLX, BL, BN> lb;
+        int ld_seg = P.seg_begin, ld_k0 = 0, ld_K = 0, ld_it = 0;
+        bool fresh = true;
+        if (n_iters > 0) {  // locate iteration it_begin
+            int skip = it_begin;
+            for (;; ++ld_seg) {
+                const int K = segs[ld_seg].K;
+                const int n = (K + BK - 1) / BK;
+                if (skip < n) {
+                    ld_k0 = skip * BK;
+                    ld_K = K;
+                    break;
                 }
-                const GemmSegment& S = segs[ld_seg];
+                skip -= n;
+            }
+        }
+        auto issue_load = [&](int stage) {
+            if (ld_it < n_iters) {
+                if (ld_k0 >= ld_K) {  // next segment with K > 0
+                    do {
+                        ++ld_seg;
+                        ld_K = segs[ld_seg].K;
+                    } while (ld_K <= 0);
+                    ld_k0 = 0;
+                    fresh = true;
+                }
+                if (fresh) {
+                    const GemmSegment& S = segs[ld_seg];
+                    la.init(g.A + S.offA * ES, S.sAm, S.sAk, P.M, T.m0, ld_k0, base_aligned && (S.align & 1), tid);
+                    lb.init(g.B + S.offB * ES, S.sBn, S.sBk, P.N, T.n0, ld_k0, base_aligned && (S.align & 2), tid);
+                    fresh = false;
+                }
                 const uint32_t sa = smem + stage * STAGE_BYTES, sb = sa + A_BYTES;
-                TileLoader<CPLX, AL, BM>::load(sa, A + S.offA * ES, S.sAm, S.sAk, P.M, S.K, T.m0, ld_k0,
-                                               base_aligned && (S.align & 1), tid);
-                TileLoader<CPLX, BL, BN>::load(sb, B + S.offB * ES, S.sBn, S.sBk, P.N, S.K, T.n0, ld_k0,
-                                               base_aligned && (S.align & 2), tid);
+                la.issue(sa, ld_K - ld_k0);
+                lb.issue(sb, ld_K - ld_k0);
                 ld_k0 += BK;
                 ++ld_it;
             }
@@ -202,22 +340,34 @@ struct TileKernel {
 #pragma unroll
         for (int s = 0; s < kStages - 1; ++s) issue_load(s);
 
-        const uint32_t sgnA = (CPLX && (flags & YB_GEMM_CONJ_A)) ? 0x80000000u : 0u;
-        const uint32_t sgnB = (CPLX && (flags & YB_GEMM_CONJ_B)) ? 0x80000000u : 0u;
+        const uint32_t sgnA = (CPLX && (g.flags & YB_GEMM_CONJ_A)) ? 0x80000000u : 0u;
+        const uint32_t sgnB = (CPLX && (g.flags & YB_GEMM_CONJ_B)) ? 0x80000000u : 0u;
 
-        for (int it = 0; it < total_iters; ++it) {
+        // per-thread fragment offsets inside a stage (k-step 0); later k-steps add a compile-time constant
+        uint32_t aoff[MT], boff[NT];
+#pragma unroll
+        for (int i = 0; i < MT; ++i) aoff[i] = frag_offset<CPLX, AL, BM>(wm0 + i * 8 + lx, lk);
+#pragma unroll
+        for (int j = 0; j < NT; ++j) boff[j] = A_BYTES + frag_offset<CPLX, BL, BN>(wn0 + j * 8 + lx, lk);
+
+        for (int it = 0; it < n_iters; ++it) {
             cp_async_wait<kStages - 2>();
             __syncthreads();
             issue_load((it + kStages - 1) % kStages);
-            const uint32_t sa = smem + (it % kStages) * STAGE_BYTES, sb = sa + A_BYTES;
+            const uint32_t sa = smem + (it % kStages) * STAGE_BYTES;
 #pragma unroll
             for (int ks = 0; ks < KSTEPS; ++ks) {
+                // the swizzle only depends on the low bits of x (KC) or of k (XC); k-step ks moves k by 4*ks:
+                //   KC: byte offset += 4*ks*ES inside the 128-byte row -> chunk index changes by a constant XOR-free add
+                //   XC: row += 4*ks rows of BX*ES bytes, swizzle term (k & 3) unchanged
                 if constexpr (!CPLX) {
                     double af[MT], bf[NT];
 #pragma unroll
-                    for (int i = 0; i < MT; ++i) af[i] = lds64(sa + frag_offset<CPLX, AL, BM>(wm0 + i * 8 + lx, ks * 4 + lk));
+                    for (int i = 0; i < MT; ++i)
+                        af[i] = lds64(sa + (AL == KC ? (aoff[i] ^ (ks * 32)) : (aoff[i] + ks * 4 * BM * ES)));
 #pragma unroll
-                    for (int j = 0; j < NT; ++j) bf[j] = lds64(sb + frag_offset<CPLX, BL, BN>(wn0 + j * 8 + lx, ks * 4 + lk));
+                    for (int j = 0; j < NT; ++j)
+                        bf[j] = lds64(sa + (BL == KC ? (boff[j] ^ (ks * 32)) : (boff[j] + ks * 4 * BN * ES)));
 #pragma unroll
                     for (int i = 0; i < MT; ++i)
 #pragma unroll
@@ -227,13 +377,13 @@ struct TileKernel {
                     double naf[MT];
 #pragma unroll
                     for (int i = 0; i < MT; ++i) {
-                        af[i] = lds128(sa + frag_offset<CPLX, AL, BM>(wm0 + i * 8 + lx, ks * 4 + lk));
+                        af[i] = lds128(sa + (AL == KC ? (aoff[i] ^ (ks * 64)) : (aoff[i] + ks * 4 * BM * ES)));
                         af[i].y = flip_sign(af[i].y, sgnA);
                         naf[i] = flip_sign(af[i].y, 0x80000000u);
                     }
 #pragma unroll
                     for (int j = 0; j < NT; ++j) {
-                        bf[j] = lds128(sb + frag_offset<CPLX, BL, BN>(wn0 + j * 8 + lx, ks * 4 + lk));
+                        bf[j] = lds128(sa + (BL == KC ? (boff[j] ^ (ks * 64)) : (boff[j] + ks * 4 * BN * ES)));
                         bf[j].y = flip_sign(bf[j].y, sgnB);
                     }
 #pragma unroll
@@ -249,12 +399,51 @@ struct TileKernel {
             }
         }
         cp_async_wait<0>();
+        __syncthreads();   // all warps are done with the stages before the next tile's prologue overwrites them
 
-        // epilogue: lane holds C[row][col], C[row][col+1] of every 8x8 tile
-        const int64_t ldc = P.ldc;
+        // ---- stream-K fix-up ---------------------------------------------------------------------
+        const bool starts = it_begin == 0, ends = it_end >= T.iters;
+        if (!starts) {
+            // contributor: publish the partial tile in this CTA's slot and leave
+            double* slot = g.ws + (size_t)blockIdx.x * kWsDoubles + tid;
+            int r = 0;
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+#pragma unroll
+                for (int j = 0; j < NT; ++j)
+#pragma unroll
+                    for (int c = 0; c < (CPLX ? 4 : 2); ++c) __stcg(slot + (r++) * kGemmThreads, acc[i][j][c]);
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) st_release(g.sync_flags + blockIdx.x, 1);
+            return;
+        }
+        if (!ends) {
+            // finisher: add the partials of the following CTAs in CTA order
+            for (int d = blockIdx.x + 1;; ++d) {
+                const CtaRange Rd = g.ranges[d];
+                if (tid == 0) {
+                    while (ld_acquire(g.sync_flags + d) == 0) __nanosleep(64);
+                    g.sync_flags[d] = 0;   // flags rest at 0 between launches (graph-replay safe)
+                }
+                __syncthreads();
+                const double* slot = g.ws + (size_t)d * kWsDoubles + tid;
+                int r = 0;
+#pragma unroll
+                for (int i = 0; i < MT; ++i)
+#pragma unroll
+                    for (int j = 0; j < NT; ++j)
+#pragma unroll
+                        for (int c = 0; c < (CPLX ? 4 : 2); ++c) acc[i][j][c] += __ldcg(slot + (r++) * kGemmThreads);
+                if (Rd.tile_end > tile_index || Rd.it_end >= T.iters) break;
+            }
+        }
+
+        // ---- epilogue: lane holds C[row][col], C[row][col+1] of every 8x8 tile ---------------------
+        const ScatterInfo* S = P.scat >= 0 ? g.scat + P.scat : nullptr;
         if constexpr (!CPLX) {
-            double* Cp = reinterpret_cast<double*>(C) + P.offC;
-            const bool vec = base_aligned && ((P.offC & 1) == 0) && ((ldc & 1) == 0);
+            double* Cp = reinterpret_cast<double*>(g.C) + P.offC;
+            const bool vec = base_aligned && ((P.offC & 1) == 0) && ((P.ldc & 1) == 0);
 #pragma unroll
             for (int i = 0; i < MT; ++i) {
                 const int row = T.m0 + wm0 + i * 8 + lx;
@@ -262,18 +451,12 @@ struct TileKernel {
 #pragma unroll
                     for (int j = 0; j < NT; ++j) {
                         const int col = T.n0 + wn0 + j * 8 + 2 * lk;
-                        double* p = Cp + row * ldc + col;
-                        if (vec && col + 1 < P.N) {
-                            *reinterpret_cast<double2*>(p) = make_double2(acc[i][j][0], acc[i][j][1]);
-                        } else {
-                            if (col < P.N) p[0] = acc[i][j][0];
-                            if (col + 1 < P.N) p[1] = acc[i][j][1];
-                        }
+                        store_pair<double>(g, P, S, Cp, row, col, acc[i][j][0], acc[i][j][1], vec);
                     }
                 }
             }
         } else {
-            double2* Cp = reinterpret_cast<double2*>(C) + P.offC;
+            double2* Cp = reinterpret_cast<double2*>(g.C) + P.offC;
 #pragma unroll
             for (int i = 0; i < MT; ++i) {
                 const int row = T.m0 + wm0 + i * 8 + lx;
@@ -281,9 +464,8 @@ struct TileKernel {
 #pragma unroll
                     for (int j = 0; j < NT; ++j) {
                         const int col = T.n0 + wn0 + j * 8 + 2 * lk;
-                        double2* p = Cp + row * ldc + col;
-                        if (col < P.N) p[0] = make_double2(acc[i][j][0], acc[i][j][2]);
-                        if (col + 1 < P.N) p[1] = make_double2(acc[i][j][1], acc[i][j][3]);
+                        store_pair<double2>(g, P, S, Cp, row, col, make_double2(acc[i][j][0], acc[i][j][2]),
+                                            make_double2(acc[i][j][1], acc[i][j][3]), false);
                     }
                 }
             }
@@ -299,19 +481,21 @@ struct GroupKernel {
 };
 
 template <bool CPLX, int AL, int BL>
-__global__ void __launch_bounds__(kGemmThreads, 2)
-gemm_kernel(const GemmProblem* __restrict__ problems, const GemmSegment* __restrict__ segs,
-            const GemmTile* __restrict__ tiles, const char* __restrict__ A, const char* __restrict__ B,
-            char* __restrict__ C, int flags, int base_aligned) {
+__global__ void __launch_bounds__(kGemmThreads, 2) gemm_kernel(const GemmArgs g) {
     extern __shared__ __align__(128) char smem_raw[];
     const uint32_t smem = (uint32_t)__cvta_generic_to_shared(smem_raw);
-    const GemmTile T = tiles[blockIdx.x];
-    const GemmProblem P = problems[T.prob];
+    const CtaRange R = g.ranges[blockIdx.x];
     using G = GroupKernel<CPLX, AL, BL>;
-    if (T.cfg == 0)
-        G::Big::run(P, segs, T, A, B, C, flags, base_aligned != 0, smem);
-    else
-        G::Small::run(P, segs, T, A, B, C, flags, base_aligned != 0, smem);
+    for (int t = R.tile_begin; t <= R.tile_end; ++t) {
+        const GemmTile T = g.tiles[t];
+        const GemmProblem P = g.problems[T.prob];
+        const int ib = (t == R.tile_begin) ? R.it_begin : 0;
+        const int ie = (t == R.tile_end) ? R.it_end : max(T.iters, 1);
+        if (T.cfg == 0)
+            G::Big::run(g, P, T, t, ib, ie, smem);
+        else
+            G::Small::run(g, P, T, t, ib, ie, smem);
+    }
 }
 
 }  // namespace yb
@@ -321,49 +505,87 @@ using namespace yb;
 struct yb_gemm_plan {
     int dtype = 0, device = 0;
     int al = KC, bl = XC;
-    int ntiles = 0;
+    int ntiles = 0, grid = 0, nsplit = 0;
     int64_t macs = 0, nbig = 0, nsmall = 0;
-    DeviceTable problems, segments, tiles;
+    DeviceTable problems, segments, tiles, ranges, scat, rowinfo, colinfo, dstpool;
+    double* ws = nullptr;   // per-device stream-K workspace (shared by all plans of the device, see device_workspace)
+    int* flags = nullptr;
 };
 
 namespace {
 
-template <bool CPLX, int AL, int BL>
-int launch(const yb_gemm_plan* p, const void* A, const void* B, void* C, int flags, int base_aligned, cudaStream_t st) {
-    using G = GroupKernel<CPLX, AL, BL>;
-    static bool configured[64] = {false};
-    if (p->device >= 0 && p->device < 64 && !configured[p->device]) {
-        YB_CUDA(cudaFuncSetAttribute(gemm_kernel<CPLX, AL, BL>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
-        configured[p->device] = true;
+// Stream-K workspace: one partial-tile slot and one flag per resident CTA.  It is shared by every plan of a
+// device (a plan cache holds thousands of plans), which is safe because launches of one device are stream-ordered
+// by the caller (YASTN runs on torch's current stream) and every launch leaves all flags at 0.
+struct DeviceWorkspace {
+    double* ws = nullptr;
+    int* flags = nullptr;
+    int slots = 0;
+};
+int device_workspace(int device, int slots, DeviceWorkspace** out) {
+    static DeviceWorkspace table[64];
+    if (device < 0 || device >= 64) return fail(kErrArg, "yb_gemm: device index %d out of range", device);
+    DeviceWorkspace& w = table[device];
+    if (w.slots < slots) {
+        if (w.ws) cudaFree(w.ws);
+        if (w.flags) cudaFree(w.flags);
+        w.ws = nullptr;
+        w.flags = nullptr;
+        w.slots = 0;
+        YB_CUDA(cudaMalloc(&w.ws, (size_t)slots * kWsDoubles * sizeof(double)));
+        YB_CUDA(cudaMalloc(&w.flags, (size_t)slots * sizeof(int)));
+        YB_CUDA(cudaMemset(w.flags, 0, (size_t)slots * sizeof(int)));
+        w.slots = slots;
     }
-    gemm_kernel<CPLX, AL, BL><<<p->ntiles, kGemmThreads, G::SMEM_BYTES, st>>>(
-        (const GemmProblem*)p->problems.ptr, (const GemmSegment*)p->segments.ptr, (const GemmTile*)p->tiles.ptr,
-        (const char*)A, (const char*)B, (char*)C, flags, base_aligned);
+    *out = &w;
+    return kOk;
+}
+
+template <bool CPLX, int AL, int BL>
+int occupancy(int device, int* blocks_per_sm) {
+    using G = GroupKernel<CPLX, AL, BL>;
+    YB_CUDA(cudaFuncSetAttribute(gemm_kernel<CPLX, AL, BL>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
+    YB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, gemm_kernel<CPLX, AL, BL>, kGemmThreads, G::SMEM_BYTES));
+    (void)device;
+    return kOk;
+}
+
+template <bool CPLX>
+int occupancy_layout(int al, int bl, int device, int* b) {
+    if (al == KC && bl == XC) return occupancy<CPLX, KC, XC>(device, b);
+    if (al == KC && bl == KC) return occupancy<CPLX, KC, KC>(device, b);
+    if (al == XC && bl == XC) return occupancy<CPLX, XC, XC>(device, b);
+    return occupancy<CPLX, XC, KC>(device, b);
+}
+
+template <bool CPLX, int AL, int BL>
+int launch(const yb_gemm_plan* p, const GemmArgs& args, cudaStream_t st) {
+    using G = GroupKernel<CPLX, AL, BL>;
+    gemm_kernel<CPLX, AL, BL><<<p->grid, kGemmThreads, G::SMEM_BYTES, st>>>(args);
     YB_CUDA(cudaGetLastError());
     return kOk;
 }
 
 template <bool CPLX>
-int dispatch_layout(const yb_gemm_plan* p, const void* A, const void* B, void* C, int flags, int ba, cudaStream_t st) {
-    if (p->al == KC && p->bl == XC) return launch<CPLX, KC, XC>(p, A, B, C, flags, ba, st);
-    if (p->al == KC && p->bl == KC) return launch<CPLX, KC, KC>(p, A, B, C, flags, ba, st);
-    if (p->al == XC && p->bl == XC) return launch<CPLX, XC, XC>(p, A, B, C, flags, ba, st);
-    return launch<CPLX, XC, KC>(p, A, B, C, flags, ba, st);
+int dispatch_layout(const yb_gemm_plan* p, const GemmArgs& args, cudaStream_t st) {
+    if (p->al == KC && p->bl == XC) return launch<CPLX, KC, XC>(p, args, st);
+    if (p->al == KC && p->bl == KC) return launch<CPLX, KC, KC>(p, args, st);
+    if (p->al == XC && p->bl == XC) return launch<CPLX, XC, XC>(p, args, st);
+    return launch<CPLX, XC, KC>(p, args, st);
 }
 
-}  // namespace
-
-extern "C" int yb_gemm_plan_create(const int64_t* problems, int64_t nprob, const int64_t* segments, int64_t nseg,
-                                   int dtype, int device, yb_gemm_plan** out) {
+int create_plan(const int64_t* problems, int64_t nprob, const int64_t* segments, int64_t nseg, const int64_t* scat_index,
+                int64_t nscat, const int64_t* row_ptr, const int64_t* row_cuts, const int64_t* col_ptr, const int64_t* col_cuts,
+                const int64_t* dst_ptr, const int64_t* dst, int dtype, int device, yb_gemm_plan** out) {
     if (!out) return fail(kErrArg, "yb_gemm_plan_create: out is null");
     *out = nullptr;
     if (dtype != YB_F64 && dtype != YB_C128) return fail(kErrUnsupported, "yb_gemm_plan_create: dtype %d", dtype);
     if (nprob < 0 || nseg < 0 || (nprob > 0 && !problems) || (nseg > 0 && !segments))
         return fail(kErrArg, "yb_gemm_plan_create: bad tables");
     const bool cplx = dtype == YB_C128;
+    const int ES = cplx ? 16 : 8, BK = cplx ? 8 : 16;
 
     // operand layouts: decided by which stride is 1; must be consistent over the plan
-    int al = KC, bl = XC;
     bool a_ok[2] = {true, true}, b_ok[2] = {true, true};
     std::vector<GemmSegment> hs((size_t)nseg);
     for (int64_t s = 0; s < nseg; ++s) {
@@ -391,6 +613,12 @@ extern "C" int yb_gemm_plan_create(const int64_t* problems, int64_t nprob, const
         if (q[4] < 0 || q[5] < q[4] || q[5] > nseg) return fail(kErrArg, "yb_gemm_plan_create: problem %lld segment range", (long long)i);
         g.seg_begin = (int32_t)q[4];
         g.seg_end = (int32_t)q[5];
+        g.scat = -1;
+        g.pad_ = 0;
+        if (scat_index) {
+            if (scat_index[i] < -1 || scat_index[i] >= nscat) return fail(kErrArg, "yb_gemm_plan_create: problem %lld scatter index", (long long)i);
+            g.scat = (int32_t)scat_index[i];
+        }
         // layout feasibility: a layout is usable when its contiguous index has unit stride (or extent <= 1)
         for (int s = g.seg_begin; s < g.seg_end; ++s) {
             const GemmSegment& sg = hs[(size_t)s];
@@ -399,12 +627,16 @@ extern "C" int yb_gemm_plan_create(const int64_t* problems, int64_t nprob, const
             a_ok[XC] = a_ok[XC] && (sg.sAm == 1 || g.M <= 1);
             b_ok[XC] = b_ok[XC] && (sg.sBn == 1 || g.N <= 1);
             b_ok[KC] = b_ok[KC] && (sg.sBk == 1 || sg.K <= 1);
+            // the loaders step through the strided dim with 32-bit byte strides
+            const int64_t lim = (1ll << 32) / (16 * ES) - 1;
+            if (sg.sAm > lim || sg.sAk > lim || sg.sBk > lim || sg.sBn > lim)
+                return fail(kErrUnsupported, "yb_gemm_plan_create: leading dimension above %lld elements", (long long)lim);
         }
     }
     if (!a_ok[KC] && !a_ok[XC]) return fail(kErrUnsupported, "yb_gemm_plan_create: operand A has no common unit-stride index");
     if (!b_ok[KC] && !b_ok[XC]) return fail(kErrUnsupported, "yb_gemm_plan_create: operand B has no common unit-stride index");
-    al = a_ok[KC] ? KC : XC;
-    bl = b_ok[XC] ? XC : KC;
+    const int al = a_ok[KC] ? KC : XC;
+    const int bl = b_ok[XC] ? XC : KC;
     // 16-byte alignment of every row start (f64 only; complex elements are 16 bytes)
     for (auto& sg : hs) {
         const int64_t a_ld = (al == KC) ? sg.sAm : sg.sAk;
@@ -413,34 +645,67 @@ extern "C" int yb_gemm_plan_create(const int64_t* problems, int64_t nprob, const
         if (((sg.offB | b_ld) & 1) == 0) sg.align |= 2;
     }
 
-    // tiles, longest first (work ~ sum of K over the problem's segments)
-    struct TW {
-        GemmTile t;
-        int64_t work;
-    };
-    std::vector<TW> tw;
-    int64_t macs = 0, nbig = 0, nsmall = 0;
+    // scatter tables (fused unmerge)
+    std::vector<ScatterInfo> hsc((size_t)nscat);
+    std::vector<int2> hrow;
+    std::vector<int4> hcol;
+    std::vector<int64_t> hdst;
+    for (int64_t s = 0; s < nscat; ++s) {
+        const int64_t nrs = row_ptr[s + 1] - row_ptr[s] - 1, ncs = col_ptr[s + 1] - col_ptr[s] - 1;
+        if (nrs < 1 || ncs < 1 || dst_ptr[s + 1] - dst_ptr[s] != nrs * ncs)
+            return fail(kErrArg, "yb_gemm_plan_create: scatter %lld has inconsistent cut / destination tables", (long long)s);
+        ScatterInfo& si = hsc[(size_t)s];
+        si.dst_off = (int64_t)hdst.size();
+        si.row_off = (int32_t)hrow.size();
+        si.col_off = (int32_t)hcol.size();
+        si.ncs = (int32_t)ncs;
+        si.pad_ = 0;
+        const int64_t* rc = row_cuts + row_ptr[s];
+        const int64_t* cc = col_cuts + col_ptr[s];
+        if (rc[0] != 0 || cc[0] != 0) return fail(kErrArg, "yb_gemm_plan_create: scatter %lld cuts must start at 0", (long long)s);
+        for (int64_t i = 0; i < nrs; ++i) {
+            if (rc[i + 1] <= rc[i]) return fail(kErrArg, "yb_gemm_plan_create: scatter %lld row cuts not increasing", (long long)s);
+            for (int64_t r = rc[i]; r < rc[i + 1]; ++r) hrow.push_back(make_int2((int)i, (int)(r - rc[i])));
+        }
+        for (int64_t j = 0; j < ncs; ++j) {
+            if (cc[j + 1] <= cc[j]) return fail(kErrArg, "yb_gemm_plan_create: scatter %lld col cuts not increasing", (long long)s);
+            for (int64_t c = cc[j]; c < cc[j + 1]; ++c) hcol.push_back(make_int4((int)j, (int)(c - cc[j]), (int)(cc[j + 1] - cc[j]), 0));
+        }
+        hdst.insert(hdst.end(), dst + dst_ptr[s], dst + dst_ptr[s + 1]);
+    }
+    for (int64_t i = 0; i < nprob; ++i) {
+        const GemmProblem& g = hp[(size_t)i];
+        if (g.scat < 0) continue;
+        const int64_t s = g.scat;
+        if (row_cuts[row_ptr[s + 1] - 1] != g.M || col_cuts[col_ptr[s + 1] - 1] != g.N)
+            return fail(kErrArg, "yb_gemm_plan_create: scatter cuts of problem %lld do not cover its %d x %d block", (long long)i, g.M, g.N);
+    }
+
+    // tiles in natural order: problem by problem, row-major inside a problem
+    std::vector<GemmTile> ht;
+    int64_t macs = 0, nbig = 0, nsmall = 0, W = 0;
     const int bigM = 64, bigN = cplx ? 64 : 128, smM = cplx ? 32 : 64, smN = cplx ? 32 : 64;
+    auto tile_weight = [](const GemmTile& t) { return std::max<int64_t>(t.iters, 1) * (t.cfg == 0 ? 2 : 1); };
     for (int64_t i = 0; i < nprob; ++i) {
         const GemmProblem& g = hp[(size_t)i];
         if (g.M == 0 || g.N == 0) continue;
-        int64_t ksum = 0;
-        for (int s = g.seg_begin; s < g.seg_end; ++s) ksum += hs[(size_t)s].K;
+        int64_t ksum = 0, iters = 0;
+        for (int s = g.seg_begin; s < g.seg_end; ++s) {
+            ksum += hs[(size_t)s].K;
+            iters += (hs[(size_t)s].K + BK - 1) / BK;
+        }
+        if (iters > 0x7fffffff) return fail(kErrUnsupported, "yb_gemm_plan_create: problem %lld contraction too long", (long long)i);
         macs += (int64_t)g.M * g.N * ksum;
         const bool big = g.N > smN && g.M > smM / 2;
         const int bm = big ? bigM : smM, bn = big ? bigN : smN;
         for (int m0 = 0; m0 < g.M; m0 += bm)
             for (int n0 = 0; n0 < g.N; n0 += bn) {
-                TW x;
-                x.t = {(int32_t)i, m0, n0, big ? 0 : 1};
-                x.work = ksum * (big ? 2 : 1);
-                tw.push_back(x);
+                GemmTile t = {(int32_t)i, m0, n0, big ? 0 : 1, (int32_t)iters, {0, 0, 0}};
+                ht.push_back(t);
+                W += tile_weight(t);
                 (big ? nbig : nsmall)++;
             }
     }
-    std::stable_sort(tw.begin(), tw.end(), [](const TW& a, const TW& b) { return a.work > b.work; });
-    std::vector<GemmTile> ht(tw.size());
-    for (size_t i = 0; i < tw.size(); ++i) ht[i] = tw[i].t;
 
     yb_gemm_plan* plan = new yb_gemm_plan();
     plan->dtype = dtype;
@@ -455,9 +720,86 @@ extern "C" int yb_gemm_plan_create(const int64_t* problems, int64_t nprob, const
     cudaGetDevice(&prev);
     int rc = kOk;
     if (cudaSetDevice(device) != cudaSuccess) rc = fail(kErrCuda, "yb_gemm_plan_create: cudaSetDevice(%d) failed", device);
+
+    // stream-K shares: one per resident CTA
+    std::vector<CtaRange> hr;
+    int max_grid = 0;
+    if (rc == kOk && !ht.empty()) {
+        int sms = 148, occ = 2;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        rc = cplx ? occupancy_layout<true>(al, bl, device, &occ) : occupancy_layout<false>(al, bl, device, &occ);
+        if (rc == kOk && occ < 1) rc = fail(kErrCuda, "yb_gemm_plan_create: kernel does not fit on an SM");
+        if (rc == kOk) {
+            const int64_t maxG = (int64_t)sms * std::min(occ, 2);
+            max_grid = (int)maxG;
+            const int64_t minShare = 16;   // weighted iterations: a share below ~8 big-tile iterations is dominated by fix-up traffic
+            const int64_t G = std::max<int64_t>(1, std::min(maxG, W / minShare));
+            const int64_t share = (W + G - 1) / G;
+            // Work line: CTA c walks its share sequentially, so at any time the G CTAs sit at the same depth of their
+            // shares.  Dealing the natural order round-robin over G bins and concatenating the bins makes those
+            // simultaneously processed tiles neighbours in the natural order: they share operand panels in L2.
+            {
+                std::vector<GemmTile> line;
+                line.reserve(ht.size());
+                for (int64_t c = 0; c < G; ++c)
+                    for (size_t i = (size_t)c; i < ht.size(); i += (size_t)G) line.push_back(ht[i]);
+                ht.swap(line);
+            }
+            std::vector<int64_t> wbegin(ht.size() + 1, 0);   // weighted start of every tile on the work line
+            for (size_t i = 0; i < ht.size(); ++i) wbegin[i + 1] = wbegin[i] + tile_weight(ht[i]);
+            // position of a cut on the work line: (tile, iteration); cuts inside tiles much smaller than a share
+            // snap to the tile start (no fix-up traffic for an imbalance below 1/16 share)
+            auto locate = [&](int64_t w, int& tile, int& it) {
+                if (w >= W) {
+                    tile = (int)ht.size();
+                    it = 0;
+                    return;
+                }
+                const size_t t = (size_t)(std::upper_bound(wbegin.begin(), wbegin.end(), w) - wbegin.begin()) - 1;
+                const int64_t tw = wbegin[t + 1] - wbegin[t];
+                tile = (int)t;
+                it = (int)((w - wbegin[t]) / (ht[t].cfg == 0 ? 2 : 1));
+                if (tw * 16 <= share || ht[t].iters <= 1) it = 0;
+            };
+            int pt = 0, pi = 0;
+            for (int64_t c = 1; c <= G; ++c) {
+                int t, i;
+                locate(std::min(W, c * share), t, i);
+                if (t == pt && i == pi) continue;   // empty share
+                CtaRange r;
+                r.tile_begin = pt;
+                r.it_begin = pi;
+                if (i == 0) {
+                    r.tile_end = t - 1;
+                    r.it_end = std::max(ht[(size_t)t - 1].iters, 1);
+                } else {
+                    r.tile_end = t;
+                    r.it_end = i;
+                }
+                hr.push_back(r);
+                if (r.it_begin > 0) plan->nsplit++;
+                pt = t;
+                pi = i;
+            }
+            plan->grid = (int)hr.size();
+        }
+    }
     if (rc == kOk) rc = plan->problems.upload(hp.data(), hp.size() * sizeof(GemmProblem));
     if (rc == kOk) rc = plan->segments.upload(hs.data(), hs.size() * sizeof(GemmSegment));
     if (rc == kOk) rc = plan->tiles.upload(ht.data(), ht.size() * sizeof(GemmTile));
+    if (rc == kOk) rc = plan->ranges.upload(hr.data(), hr.size() * sizeof(CtaRange));
+    if (rc == kOk) rc = plan->scat.upload(hsc.data(), hsc.size() * sizeof(ScatterInfo));
+    if (rc == kOk) rc = plan->rowinfo.upload(hrow.data(), hrow.size() * sizeof(int2));
+    if (rc == kOk) rc = plan->colinfo.upload(hcol.data(), hcol.size() * sizeof(int4));
+    if (rc == kOk) rc = plan->dstpool.upload(hdst.data(), hdst.size() * sizeof(int64_t));
+    if (rc == kOk && plan->nsplit > 0) {
+        DeviceWorkspace* w = nullptr;
+        rc = device_workspace(device, max_grid, &w);
+        if (rc == kOk) {
+            plan->ws = w->ws;
+            plan->flags = w->flags;
+        }
+    }
     cudaSetDevice(prev);
     if (rc != kOk) {
         yb_gemm_plan_destroy(plan);
@@ -467,12 +809,31 @@ extern "C" int yb_gemm_plan_create(const int64_t* problems, int64_t nprob, const
     return kOk;
 }
 
-extern "C" int yb_gemm_plan_info(const yb_gemm_plan* plan, int64_t info[4]) {
+}  // namespace
+
+extern "C" int yb_gemm_plan_create(const int64_t* problems, int64_t nprob, const int64_t* segments, int64_t nseg,
+                                   int dtype, int device, yb_gemm_plan** out) {
+    return create_plan(problems, nprob, segments, nseg, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, dtype, device, out);
+}
+
+extern "C" int yb_gemm_plan_create_scatter(const int64_t* problems, int64_t nprob, const int64_t* segments, int64_t nseg,
+                                           const int64_t* scat_index, int64_t nscat, const int64_t* row_ptr,
+                                           const int64_t* row_cuts, const int64_t* col_ptr, const int64_t* col_cuts,
+                                           const int64_t* dst_ptr, const int64_t* dst, int dtype, int device,
+                                           yb_gemm_plan** out) {
+    if (nscat < 0 || (nscat > 0 && (!scat_index || !row_ptr || !row_cuts || !col_ptr || !col_cuts || !dst_ptr || !dst)))
+        return fail(kErrArg, "yb_gemm_plan_create_scatter: bad scatter tables");
+    return create_plan(problems, nprob, segments, nseg, scat_index, nscat, row_ptr, row_cuts, col_ptr, col_cuts, dst_ptr, dst, dtype, device, out);
+}
+
+extern "C" int yb_gemm_plan_info(const yb_gemm_plan* plan, int64_t info[6]) {
     if (!plan || !info) return fail(kErrArg, "yb_gemm_plan_info: null argument");
     info[0] = plan->ntiles;
     info[1] = plan->macs;
     info[2] = plan->nbig;
     info[3] = plan->nsmall;
+    info[4] = plan->grid;
+    info[5] = plan->nsplit;
     return kOk;
 }
 
@@ -480,13 +841,28 @@ extern "C" int yb_gemm_run(const yb_gemm_plan* plan, const void* A, const void* 
     if (!plan) return fail(kErrArg, "yb_gemm_run: plan is null");
     if (plan->ntiles == 0) return kOk;
     if (!A || !B || !C) return fail(kErrArg, "yb_gemm_run: null data pointer");
-    const int ba = (((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15) == 0;
+    GemmArgs args;
+    args.problems = (const GemmProblem*)plan->problems.ptr;
+    args.segs = (const GemmSegment*)plan->segments.ptr;
+    args.tiles = (const GemmTile*)plan->tiles.ptr;
+    args.ranges = (const CtaRange*)plan->ranges.ptr;
+    args.scat = (const ScatterInfo*)plan->scat.ptr;
+    args.rowinfo = (const int2*)plan->rowinfo.ptr;
+    args.colinfo = (const int4*)plan->colinfo.ptr;
+    args.dstpool = (const int64_t*)plan->dstpool.ptr;
+    args.ws = plan->ws;
+    args.sync_flags = plan->flags;
+    args.A = (const char*)A;
+    args.B = (const char*)B;
+    args.C = (char*)C;
+    args.flags = flags;
+    args.base_aligned = (((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15) == 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (plan->dtype == YB_C128) {
-        if (!ba) return fail(kErrArg, "yb_gemm_run: complex128 operands must be 16-byte aligned");
-        return dispatch_layout<true>(plan, A, B, C, flags, ba, st);
+        if (!args.base_aligned) return fail(kErrArg, "yb_gemm_run: complex128 operands must be 16-byte aligned");
+        return dispatch_layout<true>(plan, args, st);
     }
-    return dispatch_layout<false>(plan, A, B, C, flags, ba, st);
+    return dispatch_layout<false>(plan, args, st);
 }
 
 extern "C" void yb_gemm_plan_destroy(yb_gemm_plan* plan) {
@@ -494,5 +870,10 @@ extern "C" void yb_gemm_plan_destroy(yb_gemm_plan* plan) {
     plan->problems.release();
     plan->segments.release();
     plan->tiles.release();
+    plan->ranges.release();
+    plan->scat.release();
+    plan->rowinfo.release();
+    plan->colinfo.release();
+    plan->dstpool.release();
     delete plan;
 }

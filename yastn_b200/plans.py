@@ -169,6 +169,58 @@ def dot_backward_tables(meta_dot):
     return f(probA, 6), f(segA, 7), f(probB, 6), f(segB, 7)
 
 
+def unmerge_scatter_tables(meta_dot, meta_unmerge):
+    """Tables of the fused unmerge epilogue (include/yastn_b200.h, yb_gemm_plan_create_scatter).
+
+    ``meta_unmerge`` (yastn/tensor/_merging.py:528-549) lists, for every merged C block ``slo`` of shape ``Do``,
+    the rectangles ``((r0, r1), (c0, c1))`` that become the output blocks at ``sln``.  The rectangles of one merged
+    block form a complete grid (row cuts x col cuts); the GEMM epilogue then writes every element straight to its
+    output block.  Returns (scat_index[nprob], row_ptr, row_cuts, col_ptr, col_cuts, dst_ptr, dst).
+    """
+    by_src = OrderedDict()
+    for sln, Dn, slo, Do, sub in meta_unmerge:
+        by_src.setdefault(slo, []).append((sln, Do, sub))
+    scat_index = np.full(len(meta_dot), -1, dtype=I64)
+    row_ptr, col_ptr, dst_ptr = [0], [0], [0]
+    row_cuts, col_cuts, dst = [], [], []
+    used = 0
+    for p, (slc, Dc, _, _, _, _) in enumerate(meta_dot):
+        recs = by_src.get(slc)
+        if recs is None:
+            if Dc[0] * Dc[1] == 0:
+                continue
+            raise ValueError("unmerge meta does not cover every block produced by dot")
+        used += 1
+        rows = sorted({sub[0] for _, _, sub in recs})
+        cols = sorted({sub[1] for _, _, sub in recs})
+        if len(rows) * len(cols) != len(recs):
+            raise ValueError("unmerge rectangles of a block do not form a grid")
+        ri = {rc: i for i, rc in enumerate(rows)}
+        ci = {cc: j for j, cc in enumerate(cols)}
+        block = np.full((len(rows), len(cols)), -1, dtype=I64)
+        for sln, Do, sub in recs:
+            if tuple(Do) != tuple(Dc):
+                raise ValueError("unmerge source shape differs from the dot block shape")
+            block[ri[sub[0]], ci[sub[1]]] = sln[0]
+        rc = [rows[0][0]] + [r[1] for r in rows]
+        cc = [cols[0][0]] + [c[1] for c in cols]
+        ok = (block >= 0).all() and rc[0] == 0 and cc[0] == 0 and rc[-1] == Dc[0] and cc[-1] == Dc[1] \
+            and all(a[1] == b[0] for a, b in zip(rows, rows[1:])) and all(a[1] == b[0] for a, b in zip(cols, cols[1:]))
+        if not ok:
+            raise ValueError("unmerge rectangles do not tile the merged block")
+        scat_index[p] = len(row_ptr) - 1
+        row_cuts += rc
+        col_cuts += cc
+        dst += block.reshape(-1).tolist()
+        row_ptr.append(len(row_cuts))
+        col_ptr.append(len(col_cuts))
+        dst_ptr.append(len(dst))
+    if used != len(by_src):
+        raise ValueError("unmerge meta references blocks that dot does not produce")
+    f = lambda x: np.array(x, dtype=I64)
+    return scat_index, f(row_ptr), f(row_cuts), f(col_ptr), f(col_cuts), f(dst_ptr), f(dst)
+
+
 def _matrix_view(Di, order, Dl, Dr):
     """Strides (row, col) of block.reshape(Di).permute(order).reshape(Dl, Dr) if it is a strided matrix, else None."""
     ext = [Di[k] for k in order]
@@ -276,20 +328,26 @@ class CopyPlan:
 class GemmPlan:
     """Device plan of one grouped-GEMM launch (owns the C handle)."""
 
-    def __init__(self, problems, segments, dtype_code, device):
+    def __init__(self, problems, segments, dtype_code, device, scatter=None):
         lib = _lib.load()
         self._lib = lib
         self.handle = ctypes.c_void_p()
         problems = np.ascontiguousarray(problems, dtype=I64)
         segments = np.ascontiguousarray(segments, dtype=I64)
-        _lib.check(lib.yb_gemm_plan_create(_ptr(problems), problems.shape[0], _ptr(segments), segments.shape[0],
-                                           dtype_code, device, ctypes.byref(self.handle)))
+        if scatter is None:
+            _lib.check(lib.yb_gemm_plan_create(_ptr(problems), problems.shape[0], _ptr(segments), segments.shape[0],
+                                               dtype_code, device, ctypes.byref(self.handle)))
+        else:
+            tabs = [np.ascontiguousarray(t, dtype=I64) for t in scatter]
+            _lib.check(lib.yb_gemm_plan_create_scatter(_ptr(problems), problems.shape[0], _ptr(segments), segments.shape[0],
+                                                       _ptr(tabs[0]), tabs[1].shape[0] - 1, *[_ptr(t) for t in tabs[1:]],
+                                                       dtype_code, device, ctypes.byref(self.handle)))
         self.device = device
 
     def info(self):
-        out = (ctypes.c_int64 * 4)()
+        out = (ctypes.c_int64 * 6)()
         _lib.check(self._lib.yb_gemm_plan_info(self.handle, out))
-        return {"tiles": out[0], "macs": out[1], "big_tiles": out[2], "small_tiles": out[3]}
+        return {"tiles": out[0], "macs": out[1], "big_tiles": out[2], "small_tiles": out[3], "grid": out[4], "split_ctas": out[5]}
 
     def run(self, a_ptr, b_ptr, c_ptr, flags, stream):
         rc = self._lib.yb_gemm_run(self.handle, a_ptr, b_ptr, c_ptr, flags, stream)
