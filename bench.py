@@ -33,6 +33,11 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 FP64_PEAK_TFLOPS = 37.1   # measured DMMA.8x8x4 pipe peak on this pool's B200 (profiles/fp64_peaks_r01.json);
                           # MEASURED_PEAKS.json carries no FP64 figure (bf16 only)
+try:
+    HBM_PEAK_GBS = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    HBM_FROM_FILE = True
+except Exception:
+    HBM_PEAK_GBS, HBM_FROM_FILE = 6650.0, False
 DEFAULT_SIZES = (1024, 2048, 4096, 8192, 16384)
 PATTERNS = ("P1", "P2")
 
@@ -156,6 +161,7 @@ def main():
     ap.add_argument("--sizes", type=int, nargs="+", default=list(DEFAULT_SIZES))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-fuse", action="store_true", help="run unmerge as its own launch instead of the GEMM scatter epilogue")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -196,16 +202,27 @@ def main():
 
     launches = [0]
 
+    fuse = not args.no_fuse
+
     def contract(w, A, B, ev=None):
+        """One fuse_to_matrix tensordot: merge A, merge B, grouped GEMM whose epilogue scatters into the unmerged
+        block layout (3 launches; with --no-fuse the unmerge is a 4th launch, exactly the reference's call sequence)."""
         st = w["stage"]
         ma, mb = st["merge_a"], st["merge_b"]
         Am, Bm = A, B
+        if ev is not None:
+            ev[2].record()
         if ma is not None:
             Am = bk.transpose_and_merge(A, ma["order"], ma["meta_new"], ma["meta_mrg"], ma["Dsize"]); launches[0] += 1
         if mb is not None:
             Bm = bk.transpose_and_merge(B, mb["order"], mb["meta_new"], mb["meta_mrg"], mb["Dsize"]); launches[0] += 1
         if ev is not None:
             ev[0].record()
+        if fuse and st["unmerge"] is not None:
+            C = bk.dot_unmerge(Am, Bm, st["dot"]["meta_dot"], st["dot"]["Dsize"], st["unmerge"]["meta"]); launches[0] += 1
+            if ev is not None:
+                ev[1].record()
+            return C
         C = bk.dot(Am, Bm, st["dot"]["meta_dot"], st["dot"]["Dsize"]); launches[0] += 1
         if ev is not None:
             ev[1].record()
@@ -227,7 +244,7 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    gemm_events = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in work] for _ in range(args.steps)]
+    gemm_events = [[tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in work] for _ in range(args.steps)]
     launches[0] = 0
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -240,7 +257,15 @@ def main():
     ms = e0.elapsed_time(e1)
     n_launch = launches[0]
     clocks = sampler.stop() if rank == 0 else None
-    gemm_ms = sum(a.elapsed_time(b) for row in gemm_events for (a, b) in row)
+    gemm_ms = sum(a.elapsed_time(b) for row in gemm_events for (a, b, _) in row)
+    merge_ms = sum(c.elapsed_time(a) for row in gemm_events for (a, _, c) in row)
+    isz = 16 if cplx else 8
+    merge_bytes = 0
+    for w in work:
+        for key in ("merge_a", "merge_b"):
+            m = w["stage"][key]
+            if m is not None:
+                merge_bytes += isz * (sum(x[1][1] - x[1][0] for x in m["meta_mrg"]) + m["Dsize"])
     own_flops = sum(w["flops"] for w in work)
 
     # end-to-end: host operands (pinned) -> H2D -> 4 backend calls -> D2H of the result
@@ -283,7 +308,7 @@ def main():
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
                 "config": {"workload": f"synthetic U(1) rank-4 block-sparse tensordot sweep (SURVEY 8d config 5): D={list(args.sizes)}, "
-                                       f"P1=A.F axes (3,0) and P2=A.B4 axes ((1,2,3),(2,1,0)), fuse_to_matrix pipeline merge/merge/GEMM/unmerge",
+                                       f"P1=A.F axes (3,0) and P2=A.B4 axes ((1,2,3),(2,1,0)), fuse_to_matrix pipeline merge/merge/GEMM+unmerge",
                            "contractions_per_step": len(work), "gflop_per_step": total_flops * 1e-9,
                            "l2": "inputs+outputs of the sweep (>10 GB) exceed L2; no flush needed",
                            "sharding": "charge sectors FLOP-balanced over ranks, no collective" if world > 1 else "single GPU"},
@@ -291,7 +316,14 @@ def main():
                 "roofline": {"kernel": "yb::gemm_kernel (grouped DMMA.8x8x4 block GEMM)", "bound": "tensor", "achieved": gemm_tflops,
                              "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": gemm_tflops / FP64_PEAK_TFLOPS, "traffic": None,
                              "peak_source": "measured FP64 DMMA pipe peak, tools/microbench/fp64_pipes.cu (profiles/fp64_peaks_r01.json); cuBLAS DGEMM 8192^3 = 35.5",
-                             "gemm_share_of_step": gemm_ms / ms if ms > 0 else None},
+                             "gemm_share_of_step": gemm_ms / ms if ms > 0 else None,
+                             "epilogue": "fused unmerge scatter" if fuse else "plain store + separate unmerge launch"},
+                "roofline_merge": {"kernel": "yb::copy_kernel (transpose_and_merge of A and B)", "bound": "hbm",
+                                   "achieved": merge_bytes * args.steps / (merge_ms * 1e-3) * 1e-9 if merge_ms > 0 else None,
+                                   "peak": HBM_PEAK_GBS, "unit": "GB/s",
+                                   "frac": merge_bytes * args.steps / (merge_ms * 1e-3) * 1e-9 / HBM_PEAK_GBS if merge_ms > 0 else None,
+                                   "share_of_step": merge_ms / ms if ms > 0 else None,
+                                   "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if HBM_FROM_FILE else "fallback 6650 GB/s (B200_PROFILING.md)"},
                 "clocks": clocks}
         if e2e is not None:
             line["e2e"] = e2e

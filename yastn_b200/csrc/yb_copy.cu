@@ -81,7 +81,7 @@ __device__ __forceinline__ void offsets_of(const REC& rec, uint32_t e, uint32_t&
 }
 
 template <typename T, bool CONJ>
-__global__ void __launch_bounds__(kCopyThreads)
+__global__ void __launch_bounds__(kCopyThreads, 3)
 copy_kernel(const CopyRec* __restrict__ recs, const CopyItem* __restrict__ items, int nitems,
             const T* __restrict__ src, T* __restrict__ dst) {
     __shared__ CopyRec srec;
@@ -115,11 +115,25 @@ copy_kernel(const CopyRec* __restrict__ recs, const CopyItem* __restrict__ items
         const T* s = src + srec.src_base;
         T* d = dst + srec.dst_base;
         if (item.kind == 0) {
+            // HBM latency x bandwidth needs ~35 KB in flight per SM: every thread keeps kUnroll independent loads
+            // outstanding before the first store (one element per thread and trip reaches only half of the bandwidth)
+            constexpr int kUnroll = 64 / sizeof(T);
             const uint32_t end = item.e0 + item.ne;
-            for (uint32_t e = item.e0 + tid; e < end; e += kCopyThreads) {
-                uint32_t so, dof;
-                offsets_of(srec, e, so, dof);
-                d[dof] = load_elem<T, CONJ>(s + so);
+            for (uint32_t e = item.e0 + tid; e < end; e += kUnroll * kCopyThreads) {
+                T v[kUnroll];
+                uint32_t dofs[kUnroll];
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) {
+                    const uint32_t ee = e + u * kCopyThreads;
+                    if (ee < end) {
+                        uint32_t so;
+                        offsets_of(srec, ee, so, dofs[u]);
+                        v[u] = load_elem<T, CONJ>(s + so);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u)
+                    if (e + u * kCopyThreads < end) d[dofs[u]] = v[u];
             }
         } else {
             // tiled transpose: slab index -> (outer index, slab coordinates along a and b)
