@@ -87,6 +87,20 @@ int yb_gemm_plan_info(const yb_gemm_plan* plan, int64_t info[6]);
 int yb_gemm_run(const yb_gemm_plan* plan, const void* A, const void* B, void* C, int flags, void* stream);
 void yb_gemm_plan_destroy(yb_gemm_plan* plan);
 
+/* ------------------------------------------------------------------------------------------------
+ * Device-side sector matching (meta pass).  All pointers are DEVICE pointers.  A blocks (table order = the reference's
+ * block order, outgoing charges first) are joined with B blocks (sorted by contracted charge first) on the contracted
+ * charge a_key / b_key ([n, key_width] int64); a_dims = [na, 2] (M, K), b_dims = [nb, 2] (K, N), *_off = block offsets.
+ * Writes, in the order of the reference's meta_dot (yastn/tensor/_contractions.py:281-346), one problem row
+ * [M, N, offC, ldc, seg, seg+1] and one segment row [K, offA, K, 1, offB, N, 1] per matching pair — the tables of
+ * yb_gemm_plan_create — and result = [pairs, C elements, status] (status 1: contracted dimensions differ, 2: more than
+ * `capacity` pairs).  scratch needs yb_match_scratch_elems(na, nb) int64.
+ * ---------------------------------------------------------------------------------------------- */
+int64_t yb_match_scratch_elems(int64_t na, int64_t nb);
+int yb_match_sectors(const int64_t* a_key, const int64_t* a_dims, const int64_t* a_off, int64_t na,
+                     const int64_t* b_key, const int64_t* b_dims, const int64_t* b_off, int64_t nb, int key_width,
+                     int64_t capacity, int64_t* problems, int64_t* segments, int64_t* result, int64_t* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,3 +70,28 @@ def test_f2m_pipeline_matches_struct_size():
     tds = case["nf"]["tds"]
     C2 = orc.transpose_dot_sum(A, B, tds["meta_dot"], tds["Areshape"], tds["Breshape"], tds["Aorder"], tds["Border"], tds["Dsize"])
     assert np.linalg.norm(C - C2) <= 1e-12 * np.linalg.norm(C)
+
+
+def _stage_blocks(stage, side):
+    m = stage["merge_a" if side == "a" else "merge_b"]
+    return None if m is None else tuple((tn, Dn, sln) for tn, Dn, sln in m["meta_new"])
+
+
+def test_meta_oracle_matches_recorded_meta_dot():
+    """The pairing oracle reproduces the meta_dot tuples the reference built for the benchmark structures (both policies)."""
+    from oracle import meta_oracle
+    checked = 0
+    for name, case in bench_structs().items():
+        nsym = case["a"]["nsym"]
+        for pol, fn in (("f2m", meta_oracle.meta_dot_f2m), ("fc", meta_oracle.meta_dot_fc)):
+            st = case.get(pol)
+            if st is None:
+                continue
+            ba, bb = _stage_blocks(st, "a"), _stage_blocks(st, "b")
+            if ba is None or bb is None:
+                continue   # the reference skipped the merge (operand already in matrix form): its block table is not recorded
+            meta_dot, t_c, D_c, size = fn(ba, bb, nsym)
+            assert meta_dot == st["dot"]["meta_dot"], (name, pol)
+            assert size == st["dot"]["Dsize"]
+            checked += 1
+    assert checked >= 10
