@@ -1,0 +1,141 @@
+#!/usr/bin/env python
+"""End-to-end DMRG on the unmodified YASTN (baseline/_ref) with a chosen backend — BASELINE.json configs 1-3 (measurement tool).
+
+    python tools/dmrg_bench.py --model heisenberg|fermions|hubbard --N 32 --D 64 --sweeps 3 --backend b200|torch|np [--device cuda]
+
+heisenberg : U(1) spin-1/2 Heisenberg chain (config 1)         float64
+fermions   : Z2 spinless-fermion hopping chain (config 2)      float64
+hubbard    : U(1)xU(1) Hubbard chain (config 3)                complex128 (--dtype) / float64
+Runs two-site DMRG (yastn/tn/mps/_dmrg.py:42-249) sweep by sweep and prints one JSON line: seconds per sweep (device
+synchronised), energy per sweep, number of hot backend calls handled by the B200 kernels, bond dimension reached.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def build(model, N, cfg_kw, yastn, mps):
+    if model == "heisenberg":
+        ops = yastn.operators.Spin12(sym="U1", **cfg_kw)
+        I = mps.product_mpo(ops.I(), N)
+        terms = []
+        for n in range(N - 1):
+            terms += [mps.Hterm(1.0, [n, n + 1], [ops.sz(), ops.sz()]), mps.Hterm(0.5, [n, n + 1], [ops.sp(), ops.sm()]),
+                      mps.Hterm(0.5, [n, n + 1], [ops.sm(), ops.sp()])]
+        n_total = 0
+    elif model == "fermions":
+        ops = yastn.operators.SpinlessFermions(sym="Z2", **cfg_kw)
+        I = mps.product_mpo(ops.I(), N)
+        terms = []
+        for n in range(N - 1):
+            terms += [mps.Hterm(-1.0, [n, n + 1], [ops.cp(), ops.c()]), mps.Hterm(-1.0, [n + 1, n], [ops.cp(), ops.c()])]
+        for n in range(N):
+            terms.append(mps.Hterm(0.2 * ((n % 3) - 1), [n], [ops.n()]))
+        n_total = (N // 2) % 2
+    else:
+        ops = yastn.operators.SpinfulFermions(sym="U1xU1", **cfg_kw)
+        I = mps.product_mpo(ops.I(), N)
+        terms = []
+        for n in range(N - 1):
+            for s in ("u", "d"):
+                terms += [mps.Hterm(-1.0, [n, n + 1], [ops.cp(s), ops.c(s)]), mps.Hterm(-1.0, [n + 1, n], [ops.cp(s), ops.c(s)])]
+        for n in range(N):
+            terms.append(mps.Hterm(4.0, [n], [ops.n("u") @ ops.n("d")]))
+        n_total = (N // 2, N // 2)
+    H = mps.generate_mpo(I, terms)
+    return ops, I, H, n_total
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--model", default="heisenberg")
+    ap.add_argument("--N", type=int, default=32)
+    ap.add_argument("--D", type=int, default=64)
+    ap.add_argument("--sweeps", type=int, default=3)
+    ap.add_argument("--backend", default="b200", choices=["b200", "torch", "np"])
+    ap.add_argument("--device", default="cuda")
+    ap.add_argument("--dtype", default="float64")
+    ap.add_argument("--policy", default="fuse_to_matrix")
+    ap.add_argument("--out", default=None)
+    ap.add_argument("--profile", action="store_true", help="time every backend function (device-synchronised: perturbs the totals)")
+    args = ap.parse_args()
+    from yastn_loader import load_yastn
+    yastn = load_yastn(allow_reference_checkout=False)
+    if yastn is None:
+        print(json.dumps({"unavailable": "yastn not importable: run tools/install_reference.sh"}))
+        return
+    import yastn.tn.mps as mps
+    counts = None
+    if args.backend == "b200":
+        from yastn_b200 import yastn_backend
+        backend = yastn_backend.module()
+        counts = yastn_backend.call_counts
+    else:
+        backend = args.backend
+    device = "cpu" if args.backend == "np" else args.device
+    prof = {}
+    if args.profile:
+        import types
+        import torch
+        if isinstance(backend, str):
+            import importlib
+            stock = importlib.import_module("yastn.backend.backend_" + backend)
+            mod = types.ModuleType("profiled_" + backend)
+            for name in dir(stock):
+                if not name.startswith("__"):
+                    setattr(mod, name, getattr(stock, name))
+            backend = mod
+
+        def wrap(name, fn):
+            def f(*a, **k):
+                if device != "cpu":
+                    torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                out = fn(*a, **k)
+                if device != "cpu":
+                    torch.cuda.synchronize()
+                e = prof.setdefault(name, [0, 0.0])
+                e[0] += 1
+                e[1] += time.perf_counter() - t0
+                return out
+            return f
+        for name in list(vars(backend)):
+            fn = getattr(backend, name)
+            if isinstance(fn, types.FunctionType) and not name.startswith("_"):
+                setattr(backend, name, wrap(name, fn))
+    cfg_kw = dict(backend=backend, default_device=device, tensordot_policy=args.policy, default_dtype=args.dtype)
+    ops, I, H, n_total = build(args.model, args.N, cfg_kw, yastn, mps)
+    ops.random_seed(seed=0)
+    psi = mps.random_mps(I, n=n_total, D_total=min(args.D, 32), dtype=args.dtype)
+    sync = (lambda: None)
+    if device != "cpu":
+        import torch
+        sync = torch.cuda.synchronize
+    times, energies = [], []
+    opts_svd = {"tol": 1e-10, "D_total": args.D}
+    t_all = time.perf_counter()
+    for out in mps.dmrg_(psi, H, method="2site", max_sweeps=args.sweeps, opts_svd=opts_svd, iterator=True):
+        sync()
+        times.append(time.perf_counter() - t_all - sum(times))
+        energies.append(float(out.energy))
+    line = {"model": args.model, "N": args.N, "D": args.D, "dtype": args.dtype, "backend": args.backend, "device": device, "policy": args.policy,
+            "sweep_s": times, "energy": energies, "bond_dims": max(psi.get_bond_dimensions()),
+            "hot_calls": counts() if counts else None}
+    if args.profile:
+        top = sorted(prof.items(), key=lambda kv: -kv[1][1])[:14]
+        line["backend_profile"] = {k: {"calls": v[0], "s": round(v[1], 3)} for k, v in top}
+        line["backend_total_s"] = round(sum(v[1] for v in prof.values()), 3)
+    print(json.dumps(line))
+    if args.out:
+        with open(args.out, "a") as f:
+            f.write(json.dumps(line) + "\n")
+
+
+if __name__ == "__main__":
+    main()

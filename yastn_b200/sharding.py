@@ -23,19 +23,64 @@ def assign_sectors(meta_dot, world):
     return owner
 
 
-def shard_f2m(stage, rank, world):
-    """Restrict the recorded metas of one fuse_to_matrix tensordot to the sectors owned by ``rank``.
+def partition_rows(meta_dot, world):
+    """FLOP-balanced assignment with row panels: lay the rows of all sectors on one line weighted by their cost (K*N per
+    row), cut it into ``world`` equal shares.  Every rank gets a contiguous run of whole sectors plus at most two partial
+    ones, balance is exact up to one row, and the result is identical on every rank (pure function of the metadata).
+    A Z2 tensor has two sectors: without row panels it cannot use more than two GPUs.
+    Returns per rank a list of (sector index, r0, r1)."""
+    cost = [Da[0] * Da[1] * Db[1] for (_, _, _, Da, _, Db) in meta_dot]
+    total = sum(cost)
+    out = [[] for _ in range(world)]
+    if total == 0:
+        out[0] = [(p, 0, rec[3][0]) for p, rec in enumerate(meta_dot)]
+        return out
+    bounds = [total * r // world for r in range(world + 1)]
+    prefix, r = 0, 0
+    for p, (slc, Dc, sla, Da, slb, Db) in enumerate(meta_dot):
+        M, per_row = Da[0], Da[1] * Db[1]
+        if cost[p] == 0:
+            out[min(r, world - 1)].append((p, 0, M))
+            continue
+        row = 0
+        while row < M:
+            # rows of this sector that still fit into rank r's share
+            room = bounds[r + 1] - (prefix + row * per_row)
+            take = M - row if r == world - 1 else min(M - row, max(0, -(-room // per_row)))
+            if take == 0:
+                r += 1
+                continue
+            out[r].append((p, row, row + take))
+            row += take
+            if r < world - 1 and prefix + row * per_row >= bounds[r + 1]:
+                r += 1
+        prefix += cost[p]
+    return out
+
+
+def shard_f2m(stage, rank, world, panels=True):
+    """Restrict the recorded metas of one fuse_to_matrix tensordot to the work units owned by ``rank``.
 
     ``stage`` = dict(merge_a, merge_b, dot, unmerge) in the reference's meta formats (None = stage skipped).
     Offsets are kept global, so shards write disjoint parts of full-size buffers and the union over ranks is
-    the unsharded result.  Returns (sharded_stage, owned_flops).
+    the unsharded result.  With ``panels`` sectors may be split into row panels (see ``partition_rows``): the ranks sharing a
+    sector each merge its operands (HBM-bound, cheap) and multiply only their rows; without, whole sectors are dealt by LPT.
+    Returns (sharded_stage, owned_flops).
     """
     meta_dot = stage["dot"]["meta_dot"]
-    owner = assign_sectors(meta_dot, world)
-    mine = [rec for rec, o in zip(meta_dot, owner) if o == rank]
-    a_slices = {rec[2] for rec in mine}
-    b_slices = {rec[4] for rec in mine}
-    c_slices = {rec[0] for rec in mine}
+    if panels:
+        units = partition_rows(meta_dot, world)[rank]
+    else:
+        units = [(p, 0, meta_dot[p][3][0]) for p, o in enumerate(assign_sectors(meta_dot, world)) if o == rank]
+    mine, a_slices, b_slices, panel_of = [], set(), set(), {}
+    for (p, r0, r1) in units:
+        slc, Dc, sla, Da, slb, Db = meta_dot[p]
+        K, N = Da[1], Db[1]
+        a_slices.add(sla)
+        b_slices.add(slb)
+        pslc = (slc[0] + r0 * N, slc[0] + r1 * N)
+        mine.append((pslc, (r1 - r0, N), (sla[0] + r0 * K, sla[0] + r1 * K), (r1 - r0, K), slb, Db))
+        panel_of.setdefault(slc, []).append((r0, r1, pslc))
     out = {"dot": {"meta_dot": tuple(mine), "Dsize": stage["dot"]["Dsize"]}}
     for key, keep in (("merge_a", a_slices), ("merge_b", b_slices)):
         m = stage[key]
@@ -46,6 +91,109 @@ def shard_f2m(stage, rank, world):
         tns = {x[0] for x in new}
         out[key] = {"order": m["order"], "meta_new": new, "meta_mrg": tuple(x for x in m["meta_mrg"] if x[0] in tns), "Dsize": m["Dsize"]}
     u = stage["unmerge"]
-    out["unmerge"] = None if u is None else {"meta": tuple(x for x in u["meta"] if x[2] in c_slices)}
+    if u is None:
+        out["unmerge"] = None
+    else:
+        # an output block is a contiguous (rows x width) rectangle: a panel owns the rows of it that fall inside [r0, r1)
+        recs = []
+        for sln, Dn, slo, Do, sub in u["meta"]:
+            (a0, a1), (c0, c1) = sub
+            w = c1 - c0
+            for r0, r1, pslc in panel_of.get(slo, ()):
+                x0, x1 = max(a0, r0), min(a1, r1)
+                if x0 >= x1:
+                    continue
+                part = (sln, Dn) if (x0, x1) == (a0, a1) else ((sln[0] + (x0 - a0) * w, sln[0] + (x1 - a0) * w), (x1 - x0, w))
+                recs.append((*part, pslc, (r1 - r0, Do[1]), ((x0 - r0, x1 - r0), sub[1])))
+        out["unmerge"] = {"meta": tuple(sorted(recs))}
     flops = sum(2 * Da[0] * Da[1] * Db[1] for (_, _, _, Da, _, Db) in mine)
     return out, flops
+
+
+def block_owner_from_sectors(meta_dot, owner, which):
+    """Owner rank of every operand / result block of a sharded fuse_to_matrix contraction.
+
+    which = 'c' (result blocks, keyed by slc), 'a' (merged A blocks, sla) or 'b' (slb).  Returns {slice: rank}.
+    """
+    pos = {"c": 0, "a": 2, "b": 4}[which]
+    return {rec[pos]: o for rec, o in zip(meta_dot, owner)}
+
+
+def exchange_plan(slices, owner_old, owner_new, rank, world):
+    """Who sends which block to whom when ownership changes between two contractions.
+
+    slices: block slices (lo, hi) of a tensor in storage order; owner_old / owner_new: rank per block (None = replicated /
+    not needed).  Returns (sends, recvs): per peer rank the list of slices to send / receive, in storage order on both sides,
+    so every rank derives matching message layouts from metadata alone (no size exchange).
+    """
+    sends = [[] for _ in range(world)]
+    recvs = [[] for _ in range(world)]
+    for sl, o_old, o_new in zip(slices, owner_old, owner_new):
+        if o_old is None or o_new is None or o_old == o_new:
+            continue
+        if o_old == rank:
+            sends[o_new].append(sl)
+        if o_new == rank:
+            recvs[o_old].append(sl)
+    return sends, recvs
+
+
+def redistribute_blocks(data, slices, owner_old, owner_new, group=None):
+    """All-to-all-v of whole blocks: after the call ``data`` (a full-size 1-D buffer on every rank) holds valid
+    blocks according to ``owner_new``.  One packed message per peer through grouped send/recv (ncclSend/ncclRecv under the
+    NCCL backend, i.e. NVLink/NVSwitch P2P on one box); message sizes follow from the block metadata on every rank.
+    """
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    sends, recvs = exchange_plan(slices, owner_old, owner_new, rank, world)
+    ops, staging = [], []
+    for peer in range(world):
+        if sends[peer]:
+            buf = torch.cat([data[lo:hi] for lo, hi in sends[peer]])
+            ops.append(dist.P2POp(dist.isend, buf, peer if group is None else dist.get_global_rank(group, peer), group))
+        if recvs[peer]:
+            n = sum(hi - lo for lo, hi in recvs[peer])
+            buf = torch.empty(n, dtype=data.dtype, device=data.device)
+            staging.append((buf, recvs[peer]))
+            ops.append(dist.P2POp(dist.irecv, buf, peer if group is None else dist.get_global_rank(group, peer), group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    for buf, sls in staging:
+        pos = 0
+        for lo, hi in sls:
+            data[lo:hi] = buf[pos:pos + hi - lo]
+            pos += hi - lo
+    return data
+
+
+def gather_blocks(data, slices, owner, group=None):
+    """Make every block valid on every rank (all-gather-v of whole blocks): used to hand a sharded result to a consumer
+    that is not sharded (e.g. the SVD of a DMRG step)."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    ops, staging = [], []
+    mine = [sl for sl, o in zip(slices, owner) if o == rank]
+    sendbuf = torch.cat([data[lo:hi] for lo, hi in mine]) if mine else None
+    for peer in range(world):
+        if peer == rank:
+            continue
+        gp = peer if group is None else dist.get_global_rank(group, peer)
+        if sendbuf is not None:
+            ops.append(dist.P2POp(dist.isend, sendbuf, gp, group))
+        theirs = [sl for sl, o in zip(slices, owner) if o == peer]
+        if theirs:
+            buf = torch.empty(sum(hi - lo for lo, hi in theirs), dtype=data.dtype, device=data.device)
+            staging.append((buf, theirs))
+            ops.append(dist.P2POp(dist.irecv, buf, gp, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    for buf, sls in staging:
+        pos = 0
+        for lo, hi in sls:
+            data[lo:hi] = buf[pos:pos + hi - lo]
+            pos += hi - lo
+    return data
