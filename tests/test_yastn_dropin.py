@@ -274,3 +274,31 @@ def test_dmrg_heisenberg_small(device):
     # N=8 open Heisenberg chain ground state energy (exact diagonalisation): -3.374932598687897
     assert abs(energies[0] - (-3.374932598687897)) < 1e-7
     assert abs(energies[1] - energies[0]) < 1e-8
+
+
+@pytest.mark.parametrize("dtype", ["float64", "complex128"])
+def test_fused_tensordot_path(device, dtype):
+    """enable_fused_tensordot(): fuse_to_matrix tensordot = merge, merge, ONE dot+unmerge launch; same tensors as the reference,
+    autograd included; backends without dot_unmerge (numpy) are untouched."""
+    ref, our = cfgs("U1", "fuse_to_matrix", device)
+    ref.backend.random_seed(23)
+    a, b = u1_operands(ref, dtype)
+    A, B = mirror(a, our), mirror(b, our)
+    yastn_backend.enable_fused_tensordot()
+    try:
+        n0 = yastn_backend.call_counts()["native"]
+        for axes in (((0, 1), (0, 1)), (0, 0), ((), ())):
+            close(yastn.tensordot(A, B, axes=axes), yastn.tensordot(a, b, axes=axes))
+        n1 = yastn_backend.call_counts()["native"]
+        assert n1["dot_unmerge"] - n0["dot_unmerge"] >= 2 and n1["unmerge"] == n0["unmerge"]
+        A.requires_grad_(True)
+        loss = yastn.tensordot(A, B, axes=(0, 0)).norm() ** 2
+        loss.backward()
+        g_fused = A._data.grad.detach().cpu().numpy().copy()
+    finally:
+        yastn_backend.disable_fused_tensordot()
+    A2 = mirror(a, our)
+    A2.requires_grad_(True)
+    (yastn.tensordot(A2, B, axes=(0, 0)).norm() ** 2).backward()
+    g_plain = A2._data.grad.detach().cpu().numpy()
+    assert np.linalg.norm(g_fused - g_plain) <= 1e-12 * np.linalg.norm(g_plain)

@@ -63,6 +63,7 @@ def main():
     ap.add_argument("--dtype", default="float64")
     ap.add_argument("--policy", default="fuse_to_matrix")
     ap.add_argument("--out", default=None)
+    ap.add_argument("--fused", action="store_true", help="b200 only: fuse dot+unmerge into one launch (yastn_backend.enable_fused_tensordot)")
     ap.add_argument("--profile", action="store_true", help="time every backend function (device-synchronised: perturbs the totals)")
     args = ap.parse_args()
     from yastn_loader import load_yastn
@@ -76,6 +77,8 @@ def main():
         from yastn_b200 import yastn_backend
         backend = yastn_backend.module()
         counts = yastn_backend.call_counts
+        if args.fused:
+            yastn_backend.enable_fused_tensordot()
     else:
         backend = args.backend
     device = "cpu" if args.backend == "np" else args.device
@@ -124,7 +127,7 @@ def main():
         sync()
         times.append(time.perf_counter() - t_all - sum(times))
         energies.append(float(out.energy))
-    line = {"model": args.model, "N": args.N, "D": args.D, "dtype": args.dtype, "backend": args.backend, "device": device, "policy": args.policy,
+    line = {"model": args.model, "N": args.N, "D": args.D, "dtype": args.dtype, "backend": args.backend + ("+fused" if args.fused else ""), "device": device, "policy": args.policy,
             "sweep_s": times, "energy": energies, "bond_dims": max(psi.get_bond_dimensions()),
             "hot_calls": counts() if counts else None}
     if args.profile:

@@ -385,38 +385,56 @@ class _TransposeDotSum(torch.autograd.Function):
 # public backend functions (names and signatures of yastn.backend.backend_torch)
 # -------------------------------------------------------------------------------------------------
 
+def _needs_grad(*tensors):
+    return torch.is_grad_enabled() and any(t.requires_grad for t in tensors)
+
+
+# autograd.Function.apply costs ~10 us of host time per call; without gradients the forward is called directly
+
 def transpose_and_merge(data, order, meta_new, meta_mrg, Dsize):
     _check(data, "transpose_and_merge")
-    return _TransposeAndMerge.apply(data, order, meta_new, meta_mrg, Dsize)
+    if _needs_grad(data):
+        return _TransposeAndMerge.apply(data, order, meta_new, meta_mrg, Dsize)
+    return _TransposeAndMerge.forward(data, order, meta_new, meta_mrg, Dsize)
 
 
 def unmerge(data, meta):
     _check(data, "unmerge")
-    return _Unmerge.apply(data, meta)
+    if _needs_grad(data):
+        return _Unmerge.apply(data, meta)
+    return _Unmerge.forward(data, meta)
 
 
 def transpose(data, axes, meta_transpose):
     _check(data, "transpose")
-    return _Transpose.apply(data, axes, meta_transpose)
+    if _needs_grad(data):
+        return _Transpose.apply(data, axes, meta_transpose)
+    return _Transpose.forward(data, axes, meta_transpose)
 
 
 def dot(Adata, Bdata, meta_dot, Dsize):
     _check(Adata, "dot")
     _check(Bdata, "dot")
-    return _Dot.apply(Adata, Bdata, meta_dot, Dsize)
+    if _needs_grad(Adata, Bdata):
+        return _Dot.apply(Adata, Bdata, meta_dot, Dsize)
+    return _Dot.forward(Adata, Bdata, meta_dot, Dsize)
 
 
 def dot_unmerge(Adata, Bdata, meta_dot, Dsize, meta_unmerge):
     """``unmerge(dot(Adata, Bdata, meta_dot, Dsize), meta_unmerge)`` in one launch (fused scatter epilogue)."""
     _check(Adata, "dot_unmerge")
     _check(Bdata, "dot_unmerge")
-    return _DotUnmerge.apply(Adata, Bdata, meta_dot, Dsize, meta_unmerge)
+    if _needs_grad(Adata, Bdata):
+        return _DotUnmerge.apply(Adata, Bdata, meta_dot, Dsize, meta_unmerge)
+    return _DotUnmerge.forward(Adata, Bdata, meta_dot, Dsize, meta_unmerge)
 
 
 def transpose_dot_sum(Adata, Bdata, meta_dot, Areshape, Breshape, Aorder, Border, Dsize):
     _check(Adata, "transpose_dot_sum")
     _check(Bdata, "transpose_dot_sum")
-    return _TransposeDotSum.apply(Adata, Bdata, meta_dot, Areshape, Breshape, Aorder, Border, Dsize)
+    if _needs_grad(Adata, Bdata):
+        return _TransposeDotSum.apply(Adata, Bdata, meta_dot, Areshape, Breshape, Aorder, Border, Dsize)
+    return _tds_forward(Adata, Bdata, meta_dot, Areshape, Breshape, Aorder, Border, Dsize)
 
 
 HOT_FUNCTIONS = ("transpose_and_merge", "unmerge", "transpose", "dot", "transpose_dot_sum")

@@ -28,7 +28,25 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+FLATTEN_SRC = os.path.join(CSRC, "yb_flatten.c")
+FLATTEN_LIB = os.path.join(HERE, "_flatten.so")
+
+
+def build_flatten(force=False):
+    """The CPython helper that flattens YASTN's nested meta tuples (host side of plan construction)."""
+    if not force and os.path.exists(FLATTEN_LIB) and os.path.getmtime(FLATTEN_LIB) >= os.path.getmtime(FLATTEN_SRC):
+        return FLATTEN_LIB
+    import sysconfig
+    inc = sysconfig.get_paths()["include"]
+    r = subprocess.run(["gcc", "-O2", "-shared", "-fPIC", "-I", inc, FLATTEN_SRC, "-o", FLATTEN_LIB], capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("gcc failed on yb_flatten.c")
+    return FLATTEN_LIB
+
+
 def build(force=False, verbose=False):
+    build_flatten(force)
     if not force and not needs_build():
         return LIB
     objs = []

@@ -24,19 +24,29 @@ int fail(int code, const char* fmt, ...);
             return yb::fail(yb::kErrCuda, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), __FILE__, __LINE__); \
     } while (0)
 
-// Owns one device allocation holding a host-built table.
+// Device memory for plan tables comes from a per-device pool (power-of-two size classes, blocks are recycled when plans
+// are destroyed) and is filled through a dedicated non-blocking copy stream: building a plan neither calls cudaMalloc in
+// steady state nor synchronises with the kernels already queued on the caller's stream (a plain cudaMemcpy would: it
+// runs on the legacy default stream).
+int pool_alloc(int device, size_t bytes, void** ptr, size_t* cap);
+void pool_free(int device, void* ptr, size_t cap);
+int pool_upload(int device, void* dst, const void* host, size_t bytes);
+
+// Owns one device allocation holding a host-built table (the current device must be the plan's device).
 struct DeviceTable {
     void* ptr = nullptr;
-    size_t bytes = 0;
+    size_t bytes = 0, cap = 0;
+    int device = 0;
     int upload(const void* host, size_t nbytes) {
         bytes = nbytes;
         if (nbytes == 0) return kOk;
-        YB_CUDA(cudaMalloc(&ptr, nbytes));
-        YB_CUDA(cudaMemcpy(ptr, host, nbytes, cudaMemcpyHostToDevice));
-        return kOk;
+        if (cudaGetDevice(&device) != cudaSuccess) return fail(kErrCuda, "cudaGetDevice failed");
+        int rc = pool_alloc(device, nbytes, &ptr, &cap);
+        if (rc != kOk) return rc;
+        return pool_upload(device, ptr, host, nbytes);
     }
     void release() {
-        if (ptr) cudaFree(ptr);
+        if (ptr) pool_free(device, ptr, cap);
         ptr = nullptr;
     }
 };

@@ -45,9 +45,11 @@ struct CopyItem {
     int32_t pad_[3];
 };
 
-struct HostRec {
+constexpr int kHostDims = 24;   // rank limit of an input record (YASTN tensors have at most ~12 legs)
+struct HostRec {                 // fixed arrays: plan construction handles thousands of records, no per-record heap traffic
     int64_t src_base, dst_base;
-    std::vector<int64_t> ext, sstr, dstr;
+    int nd;
+    int64_t ext[kHostDims], sstr[kHostDims], dstr[kHostDims];
 };
 
 __device__ __forceinline__ uint32_t fdiv(uint32_t n, uint32_t d, uint32_t mul, uint32_t shr) {
@@ -195,63 +197,82 @@ namespace {
 
 // Drop unit dims, order by destination stride (descending), merge dims that are contiguous on both sides.
 bool normalise(HostRec& r) {
-    std::vector<int> keep;
-    for (size_t k = 0; k < r.ext.size(); ++k) {
+    int keep[kHostDims], nk = 0;
+    for (int k = 0; k < r.nd; ++k) {
         if (r.ext[k] == 0) return false;
-        if (r.ext[k] != 1) keep.push_back((int)k);
+        if (r.ext[k] != 1) keep[nk++] = k;
     }
-    std::stable_sort(keep.begin(), keep.end(), [&](int a, int b) { return r.dstr[a] > r.dstr[b]; });
-    std::vector<int64_t> e, s, d;
-    for (int k : keep) {
-        if (!e.empty() && s.back() == r.sstr[k] * r.ext[k] && d.back() == r.dstr[k] * r.ext[k]) {
-            e.back() *= r.ext[k];
-            s.back() = r.sstr[k];
-            d.back() = r.dstr[k];
+    // stable insertion sort by destination stride, descending (nk is tiny)
+    for (int i = 1; i < nk; ++i) {
+        const int v = keep[i];
+        int j = i - 1;
+        while (j >= 0 && r.dstr[keep[j]] < r.dstr[v]) {
+            keep[j + 1] = keep[j];
+            --j;
+        }
+        keep[j + 1] = v;
+    }
+    int64_t e[kHostDims], s[kHostDims], d[kHostDims];
+    int n = 0;
+    for (int i = 0; i < nk; ++i) {
+        const int k = keep[i];
+        if (n > 0 && s[n - 1] == r.sstr[k] * r.ext[k] && d[n - 1] == r.dstr[k] * r.ext[k]) {
+            e[n - 1] *= r.ext[k];
+            s[n - 1] = r.sstr[k];
+            d[n - 1] = r.dstr[k];
         } else {
-            e.push_back(r.ext[k]);
-            s.push_back(r.sstr[k]);
-            d.push_back(r.dstr[k]);
+            e[n] = r.ext[k];
+            s[n] = r.sstr[k];
+            d[n] = r.dstr[k];
+            ++n;
         }
     }
-    if (e.empty()) {  // single element
-        e.push_back(1);
-        s.push_back(1);
-        d.push_back(1);
+    if (n == 0) {  // single element
+        e[0] = s[0] = d[0] = 1;
+        n = 1;
     }
-    r.ext = e;
-    r.sstr = s;
-    r.dstr = d;
+    r.nd = n;
+    for (int k = 0; k < n; ++k) {
+        r.ext[k] = e[k];
+        r.sstr[k] = s[k];
+        r.dstr[k] = d[k];
+    }
     return true;
+}
+
+void drop_front(HostRec& r) {
+    for (int k = 1; k < r.nd; ++k) {
+        r.ext[k - 1] = r.ext[k];
+        r.sstr[k - 1] = r.sstr[k];
+        r.dstr[k - 1] = r.dstr[k];
+    }
+    if (--r.nd == 0) {
+        r.ext[0] = r.sstr[0] = r.dstr[0] = 1;
+        r.nd = 1;
+    }
 }
 
 // Split records that violate device limits (rank, 31-bit element counts / relative offsets).
 void split_to_limits(const HostRec& r, std::vector<HostRec>& out) {
     int64_t total = 1, smax = 0, dmax = 0;
-    for (size_t k = 0; k < r.ext.size(); ++k) {
+    for (int k = 0; k < r.nd; ++k) {
         total *= r.ext[k];
         smax += (r.ext[k] - 1) * r.sstr[k];
         dmax += (r.ext[k] - 1) * r.dstr[k];
     }
     const int64_t lim = (1ll << 31) - 1;
-    if ((int)r.ext.size() <= kMaxDims && total <= lim && smax <= lim && dmax <= lim) {
+    if (r.nd <= kMaxDims && total <= lim && smax <= lim && dmax <= lim) {
         out.push_back(r);
         return;
     }
     // peel the outermost dim: either one index at a time (rank too high) or in two halves (too large)
     const int64_t e0 = r.ext[0];
-    if ((int)r.ext.size() > kMaxDims || e0 == 1) {
+    if (r.nd > kMaxDims || e0 == 1) {
         for (int64_t i = 0; i < e0; ++i) {
             HostRec sub = r;
             sub.src_base += i * r.sstr[0];
             sub.dst_base += i * r.dstr[0];
-            sub.ext.erase(sub.ext.begin());
-            sub.sstr.erase(sub.sstr.begin());
-            sub.dstr.erase(sub.dstr.begin());
-            if (sub.ext.empty()) {
-                sub.ext.push_back(1);
-                sub.sstr.push_back(1);
-                sub.dstr.push_back(1);
-            }
+            drop_front(sub);
             split_to_limits(sub, out);
         }
         return;
@@ -272,18 +293,23 @@ extern "C" int yb_copy_plan_create(const int64_t* recs, int64_t nrec, int rank, 
     if (!out) return fail(kErrArg, "yb_copy_plan_create: out is null");
     *out = nullptr;
     if (nrec < 0 || rank < 0 || (nrec > 0 && !recs)) return fail(kErrArg, "yb_copy_plan_create: bad table");
+    if (rank > kHostDims) return fail(kErrUnsupported, "yb_copy_plan_create: rank %d above %d", rank, kHostDims);
     if (itemsize != 8 && itemsize != 16) return fail(kErrUnsupported, "yb_copy_plan_create: itemsize %d (8 or 16)", itemsize);
 
     std::vector<HostRec> host;
+    host.reserve((size_t)nrec);
     const int64_t w = 2 + 3 * (int64_t)rank;
     for (int64_t i = 0; i < nrec; ++i) {
         const int64_t* p = recs + i * w;
         HostRec r;
         r.src_base = p[0];
         r.dst_base = p[1];
-        r.ext.assign(p + 2, p + 2 + rank);
-        r.sstr.assign(p + 2 + rank, p + 2 + 2 * rank);
-        r.dstr.assign(p + 2 + 2 * rank, p + 2 + 3 * rank);
+        r.nd = rank;
+        for (int k = 0; k < rank; ++k) {
+            r.ext[k] = p[2 + k];
+            r.sstr[k] = p[2 + rank + k];
+            r.dstr[k] = p[2 + 2 * rank + k];
+        }
         for (int k = 0; k < rank; ++k)
             if (r.ext[k] < 0 || r.sstr[k] < 0 || r.dstr[k] < 0) return fail(kErrArg, "yb_copy_plan_create: negative extent/stride in record %lld", (long long)i);
         if (!normalise(r)) continue;
@@ -302,7 +328,7 @@ extern "C" int yb_copy_plan_create(const int64_t* recs, int64_t nrec, int rank, 
         memset(&c, 0, sizeof(c));
         c.src_base = h.src_base;
         c.dst_base = h.dst_base;
-        c.nd = (int)h.ext.size();
+        c.nd = h.nd;
         int64_t total = 1;
         for (int k = 0; k < kMaxDims; ++k) {
             c.ext[k] = 1;
@@ -385,8 +411,13 @@ extern "C" int yb_copy_plan_create(const int64_t* recs, int64_t nrec, int rank, 
     if (rc == kOk) rc = plan->recs.upload(drecs.data(), drecs.size() * sizeof(CopyRec));
     if (rc == kOk) rc = plan->items.upload(items.data(), items.size() * sizeof(CopyItem));
     if (rc == kOk) {
-        int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        static int sm_count[64] = {0};
+        int sms = (device >= 0 && device < 64) ? sm_count[device] : 0;
+        if (sms == 0) {
+            sms = 148;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+            if (device >= 0 && device < 64) sm_count[device] = sms;
+        }
         plan->grid = std::max(1, std::min(plan->nitems, sms * 8));
     }
     cudaSetDevice(prev);

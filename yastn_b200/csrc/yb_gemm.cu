@@ -20,6 +20,7 @@
 // complex128 uses the 4M scheme on the same pipe: Cr += Ar*Br - Ai*Bi ; Ci += Ar*Bi + Ai*Br, with
 // conjugation of either operand folded into the fragment loads (torch's lazy conj bit).
 #include <algorithm>
+#include <type_traits>
 
 #include "yb_common.h"
 
@@ -248,33 +249,6 @@ struct TileKernel {
     static constexpr int SMEM_BYTES = STAGE_BYTES * kStages;
     static_assert(NACC <= 64, "workspace slot too small");
 
-    // Store one (row, col) / (row, col+1) accumulator pair.
-    template <typename T>
-    __device__ __forceinline__ static void store_pair(const GemmArgs& g, const GemmProblem& P, const ScatterInfo* S, T* Cbase,
-                                                      int row, int col, T v0, T v1, bool vec_ok) {
-        if (S == nullptr) {
-            T* p = Cbase + (int64_t)row * P.ldc + col;
-            if (!CPLX && vec_ok && col + 1 < P.N) {
-                *reinterpret_cast<double2*>(p) = make_double2(*reinterpret_cast<double*>(&v0), *reinterpret_cast<double*>(&v1));
-            } else {
-                if (col < P.N) p[0] = v0;
-                if (col + 1 < P.N) p[1] = v1;
-            }
-        } else {
-            const int2 ri = g.rowinfo[S->row_off + row];
-            const int64_t* dst = g.dstpool + S->dst_off + (int64_t)ri.x * S->ncs;
-            T* out = reinterpret_cast<T*>(g.C);
-            if (col < P.N) {
-                const int4 ci = g.colinfo[S->col_off + col];
-                out[dst[ci.x] + (int64_t)ri.y * ci.z + ci.y] = v0;
-            }
-            if (col + 1 < P.N) {
-                const int4 ci = g.colinfo[S->col_off + col + 1];
-                out[dst[ci.x] + (int64_t)ri.y * ci.z + ci.y] = v1;
-            }
-        }
-    }
-
     // Run k-iterations [it_begin, it_end) of tile T; handles the stream-K fix-up and the epilogue.
     __device__ static void run(const GemmArgs& g, const GemmProblem& P, const GemmTile& T, int tile_index, int it_begin, int it_end,
                                uint32_t smem) {
@@ -440,10 +414,14 @@ struct TileKernel {
         }
 
         // ---- epilogue: lane holds C[row][col], C[row][col+1] of every 8x8 tile ---------------------
-        const ScatterInfo* S = P.scat >= 0 ? g.scat + P.scat : nullptr;
-        if constexpr (!CPLX) {
-            double* Cp = reinterpret_cast<double*>(g.C) + P.offC;
-            const bool vec = base_aligned && ((P.offC & 1) == 0) && ((P.ldc & 1) == 0);
+        using T2 = typename std::conditional<CPLX, double2, double>::type;
+        auto value = [&](int i, int j, int e) -> T2 {
+            if constexpr (CPLX) return make_double2(acc[i][j][e], acc[i][j][2 + e]);
+            else return acc[i][j][e];
+        };
+        if (P.scat < 0) {
+            T2* Cp = reinterpret_cast<T2*>(g.C) + P.offC;
+            const bool vec = !CPLX && base_aligned && ((P.offC & 1) == 0) && ((P.ldc & 1) == 0);
 #pragma unroll
             for (int i = 0; i < MT; ++i) {
                 const int row = T.m0 + wm0 + i * 8 + lx;
@@ -451,21 +429,39 @@ struct TileKernel {
 #pragma unroll
                     for (int j = 0; j < NT; ++j) {
                         const int col = T.n0 + wn0 + j * 8 + 2 * lk;
-                        store_pair<double>(g, P, S, Cp, row, col, acc[i][j][0], acc[i][j][1], vec);
+                        T2* p = Cp + (int64_t)row * P.ldc + col;
+                        if constexpr (!CPLX) {
+                            if (vec && col + 1 < P.N) {
+                                *reinterpret_cast<double2*>(p) = make_double2(acc[i][j][0], acc[i][j][1]);
+                                continue;
+                            }
+                        }
+                        if (col < P.N) p[0] = value(i, j, 0);
+                        if (col + 1 < P.N) p[1] = value(i, j, 1);
                     }
                 }
             }
         } else {
-            double2* Cp = reinterpret_cast<double2*>(g.C) + P.offC;
+            // fused unmerge: the row lookups are shared by the NT column pairs of a row and the column lookups by the MT rows
+            const ScatterInfo S = g.scat[P.scat];
+            T2* out = reinterpret_cast<T2*>(g.C);
+            int2 ri[MT];
 #pragma unroll
             for (int i = 0; i < MT; ++i) {
                 const int row = T.m0 + wm0 + i * 8 + lx;
-                if (row < P.M) {
+                ri[i] = row < P.M ? g.rowinfo[S.row_off + row] : make_int2(-1, 0);
+            }
+            const int64_t* dst = g.dstpool + S.dst_off;
 #pragma unroll
-                    for (int j = 0; j < NT; ++j) {
-                        const int col = T.n0 + wn0 + j * 8 + 2 * lk;
-                        store_pair<double2>(g, P, S, Cp, row, col, make_double2(acc[i][j][0], acc[i][j][2]),
-                                            make_double2(acc[i][j][1], acc[i][j][3]), false);
+            for (int j = 0; j < NT; ++j) {
+                const int col = T.n0 + wn0 + j * 8 + 2 * lk;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    if (col + e < P.N) {
+                        const int4 ci = g.colinfo[S.col_off + col + e];
+#pragma unroll
+                        for (int i = 0; i < MT; ++i)
+                            if (ri[i].x >= 0) out[dst[(int64_t)ri[i].x * S.ncs + ci.x] + (int64_t)ri[i].y * ci.z + ci.y] = value(i, j, e);
                     }
                 }
             }
@@ -544,9 +540,14 @@ int device_workspace(int device, int slots, DeviceWorkspace** out) {
 template <bool CPLX, int AL, int BL>
 int occupancy(int device, int* blocks_per_sm) {
     using G = GroupKernel<CPLX, AL, BL>;
+    static int cached[64] = {0};   // per device: the attribute has to be set once per context, the answer never changes
+    if (device >= 0 && device < 64 && cached[device] > 0) {
+        *blocks_per_sm = cached[device];
+        return kOk;
+    }
     YB_CUDA(cudaFuncSetAttribute(gemm_kernel<CPLX, AL, BL>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
     YB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, gemm_kernel<CPLX, AL, BL>, kGemmThreads, G::SMEM_BYTES));
-    (void)device;
+    if (device >= 0 && device < 64) cached[device] = *blocks_per_sm;
     return kOk;
 }
 

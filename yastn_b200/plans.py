@@ -18,8 +18,19 @@ from collections import OrderedDict
 import numpy as np
 
 from . import _lib
+from ._flatten import flatten as _flatten_bytes      # CPython helper built by yastn_b200.build (csrc/yb_flatten.c)
 
 I64 = np.int64
+
+
+def _table(meta, n):
+    """Nested meta tuples of n equally-shaped records -> [n, width] int64 array (depth-first flattening in C)."""
+    flat = np.frombuffer(_flatten_bytes(meta), dtype=I64)
+    if n == 0:
+        return flat.reshape(0, 0)
+    if flat.size % n:
+        raise ValueError("meta records do not have a common width")
+    return flat.reshape(n, flat.size // n)
 
 
 def _cstrides(shape):
@@ -48,14 +59,27 @@ def merge_records(order, meta_new, meta_mrg):
     r = len(order)
     if n == 0:
         return np.zeros((0, 2 + 3 * max(r, 1)), dtype=I64), max(r, 1), 0
-    target = {tn: (Dn, sln[0]) for tn, Dn, sln in meta_new}
     g = len(meta_mrg[0][3])
-    Do = np.array([m[2] for m in meta_mrg], dtype=I64).reshape(n, r)
-    lo = np.array([[s[0] for s in m[3]] for m in meta_mrg], dtype=I64).reshape(n, g)
-    Drsh = np.array([m[4] for m in meta_mrg], dtype=I64).reshape(n, g)
-    Dn = np.array([target[m[0]][0] for m in meta_mrg], dtype=I64).reshape(n, g)
-    sln0 = np.array([target[m[0]][1] for m in meta_mrg], dtype=I64)
-    slo0 = np.array([m[1][0] for m in meta_mrg], dtype=I64)
+    T = len(meta_mrg[0][0])
+    mrg = _table(meta_mrg, n)                          # [tn(T), slo(2), Do(r), Dslc(2g), Drsh(g)]
+    new = _table(meta_new, len(meta_new))              # [tn(T), Dn(g), sln(2)]
+    if mrg.shape[1] != T + 2 + r + 3 * g or new.shape[1] != T + g + 2:
+        raise ValueError("transpose_and_merge: unexpected meta layout")
+    # meta_mrg is grouped by target charge in the order of meta_new (the reference relies on it: itertools.groupby in
+    # _backend_torch_backwards.py:358); fall back to a dictionary when a caller hands over another order
+    tn_m = mrg[:, :T]
+    grp = np.zeros(n, dtype=I64)
+    if n > 1 and T > 0:
+        grp[1:] = np.cumsum((tn_m[1:] != tn_m[:-1]).any(axis=1))
+    if grp[-1] >= new.shape[0] or not np.array_equal(new[grp, :T], tn_m):
+        index = {tn: i for i, (tn, _, _) in enumerate(meta_new)}
+        grp = np.array([index[m[0]] for m in meta_mrg], dtype=I64)
+    Do = mrg[:, T + 2:T + 2 + r]
+    lo = mrg[:, T + 2 + r:T + 2 + r + 2 * g:2]
+    Drsh = mrg[:, T + 2 + r + 2 * g:]
+    Dn = new[grp, T:T + g]
+    sln0 = new[grp, T + g]
+    slo0 = mrg[:, T]
     if r == 0:  # rank-0 tensor: one element per record
         one = np.ones((n, 1), dtype=I64)
         recs, rank = _pack(slo0, sln0, one, one, one)
@@ -85,33 +109,39 @@ def unmerge_records(meta):
     n = len(meta)
     if n == 0:
         return np.zeros((0, 5), dtype=I64), 1
-    g = len(meta[0][3])
+    g, gn = len(meta[0][3]), len(meta[0][1])
+    tab = _table(meta, n)                              # [sln(2), Dn(gn), slo(2), Do(g), sub(2g)]
+    if tab.shape[1] != 4 + gn + 3 * g:
+        raise ValueError("unmerge: unexpected meta layout")
+    sln0, slo0 = tab[:, 0], tab[:, 2 + gn]
     if g == 0:
         one = np.ones((n, 1), dtype=I64)
-        return _pack(np.array([m[2][0] for m in meta], dtype=I64), np.array([m[0][0] for m in meta], dtype=I64), one, one, one)
-    Do = np.array([m[3] for m in meta], dtype=I64).reshape(n, g)
-    lo = np.array([[s[0] for s in m[4]] for m in meta], dtype=I64).reshape(n, g)
-    hi = np.array([[s[1] for s in m[4]] for m in meta], dtype=I64).reshape(n, g)
+        return _pack(slo0, sln0, one, one, one)
+    Do = tab[:, 4 + gn:4 + gn + g]
+    lo = tab[:, 4 + gn + g::2]
+    hi = tab[:, 5 + gn + g::2]
     ext = hi - lo
     sstr = _cstrides(Do)
-    src_base = np.array([m[2][0] for m in meta], dtype=I64) + (lo * sstr).sum(axis=1)
-    dst_base = np.array([m[0][0] for m in meta], dtype=I64)
-    return _pack(src_base, dst_base, ext, sstr, _cstrides(ext))
+    return _pack(slo0 + (lo * sstr).sum(axis=1), sln0, ext, sstr, _cstrides(ext))
 
 
 def transpose_records(axes, meta):
     """Copy records of transpose: out[sln].view(Dn) = in[slo].view(Do).permute(axes)."""
     n = len(meta)
     r = len(axes)
-    if n == 0 or r == 0:
+    if n == 0:
+        return np.zeros((0, 5), dtype=I64), 1
+    tab = _table(meta, n)                              # [sln(2), Dn(r), slo(2), Do(r)]
+    if tab.shape[1] != 4 + 2 * r:
+        raise ValueError("transpose: unexpected meta layout")
+    sln0, slo0 = tab[:, 0], tab[:, 2 + r]
+    if r == 0:
         one = np.ones((n, 1), dtype=I64)
-        return _pack(np.array([m[2][0] for m in meta], dtype=I64), np.array([m[0][0] for m in meta], dtype=I64), one, one, one)
-    Do = np.array([m[3] for m in meta], dtype=I64).reshape(n, r)
+        return _pack(slo0, sln0, one, one, one)
+    Do = tab[:, 4 + r:]
     axes = list(axes)
     ext = Do[:, axes]
-    sstr = _cstrides(Do)[:, axes]
-    return _pack(np.array([m[2][0] for m in meta], dtype=I64), np.array([m[0][0] for m in meta], dtype=I64),
-                 ext, sstr, _cstrides(ext))
+    return _pack(slo0, sln0, ext, _cstrides(Do)[:, axes], _cstrides(ext))
 
 
 def reverse_records(recs, rank):
@@ -128,11 +158,16 @@ def dot_tables(meta_dot):
     n = len(meta_dot)
     problems = np.empty((n, 6), dtype=I64)
     segments = np.empty((n, 7), dtype=I64)
-    for i, (slc, Dc, sla, Da, slb, Db) in enumerate(meta_dot):
-        M, K = Da
-        N = Db[1]
-        problems[i] = (M, N, slc[0], N, i, i + 1)
-        segments[i] = (K, sla[0], K, 1, slb[0], N, 1)
+    if n == 0:
+        return problems, segments
+    tab = _table(meta_dot, n)                          # [slc(2), Dc(2), sla(2), Da(2), slb(2), Db(2)]
+    if tab.shape[1] != 12:
+        raise ValueError("dot: unexpected meta layout")
+    M, K, N = tab[:, 6], tab[:, 7], tab[:, 11]
+    idx = np.arange(n, dtype=I64)
+    problems[:, 0], problems[:, 1], problems[:, 2], problems[:, 3], problems[:, 4], problems[:, 5] = M, N, tab[:, 0], N, idx, idx + 1
+    segments[:, 0], segments[:, 1], segments[:, 2], segments[:, 3] = K, tab[:, 4], K, 1
+    segments[:, 4], segments[:, 5], segments[:, 6] = tab[:, 8], N, 1
     return problems, segments
 
 
@@ -177,48 +212,71 @@ def unmerge_scatter_tables(meta_dot, meta_unmerge):
     block form a complete grid (row cuts x col cuts); the GEMM epilogue then writes every element straight to its
     output block.  Returns (scat_index[nprob], row_ptr, row_cuts, col_ptr, col_cuts, dst_ptr, dst).
     """
-    by_src = OrderedDict()
-    for sln, Dn, slo, Do, sub in meta_unmerge:
-        by_src.setdefault(slo, []).append((sln, Do, sub))
-    scat_index = np.full(len(meta_dot), -1, dtype=I64)
-    row_ptr, col_ptr, dst_ptr = [0], [0], [0]
-    row_cuts, col_cuts, dst = [], [], []
-    used = 0
-    for p, (slc, Dc, _, _, _, _) in enumerate(meta_dot):
-        recs = by_src.get(slc)
-        if recs is None:
-            if Dc[0] * Dc[1] == 0:
-                continue
+    nprob, n = len(meta_dot), len(meta_unmerge)
+    if n == 0:
+        if any(rec[1][0] * rec[1][1] for rec in meta_dot):
             raise ValueError("unmerge meta does not cover every block produced by dot")
-        used += 1
-        rows = sorted({sub[0] for _, _, sub in recs})
-        cols = sorted({sub[1] for _, _, sub in recs})
-        if len(rows) * len(cols) != len(recs):
-            raise ValueError("unmerge rectangles of a block do not form a grid")
-        ri = {rc: i for i, rc in enumerate(rows)}
-        ci = {cc: j for j, cc in enumerate(cols)}
-        block = np.full((len(rows), len(cols)), -1, dtype=I64)
-        for sln, Do, sub in recs:
-            if tuple(Do) != tuple(Dc):
-                raise ValueError("unmerge source shape differs from the dot block shape")
-            block[ri[sub[0]], ci[sub[1]]] = sln[0]
-        rc = [rows[0][0]] + [r[1] for r in rows]
-        cc = [cols[0][0]] + [c[1] for c in cols]
-        ok = (block >= 0).all() and rc[0] == 0 and cc[0] == 0 and rc[-1] == Dc[0] and cc[-1] == Dc[1] \
-            and all(a[1] == b[0] for a, b in zip(rows, rows[1:])) and all(a[1] == b[0] for a, b in zip(cols, cols[1:]))
-        if not ok:
-            raise ValueError("unmerge rectangles do not tile the merged block")
-        scat_index[p] = len(row_ptr) - 1
-        row_cuts += rc
-        col_cuts += cc
-        dst += block.reshape(-1).tolist()
-        row_ptr.append(len(row_cuts))
-        col_ptr.append(len(col_cuts))
-        dst_ptr.append(len(dst))
-    if used != len(by_src):
+        z = np.zeros(1, dtype=I64)
+        return np.full(nprob, -1, dtype=I64), z, np.zeros(0, dtype=I64), z, np.zeros(0, dtype=I64), z, np.zeros(0, dtype=I64)
+    gn = len(meta_unmerge[0][1])
+    if len(meta_unmerge[0][3]) != 2:
+        raise ValueError("fused unmerge needs matrix-shaped source blocks")
+    um = _table(meta_unmerge, n)                       # [sln(2), Dn(gn), slo(2), Do(2), r0, r1, c0, c1]
+    md = _table(meta_dot, nprob)
+    sln0, slo0 = um[:, 0], um[:, 2 + gn]
+    DoM, DoN = um[:, 4 + gn], um[:, 5 + gn]
+    r0, r1, c0, c1 = (um[:, 6 + gn + k] for k in range(4))
+    src, grp = np.unique(slo0, return_inverse=True)    # merged blocks that are unmerged, and the group of every record
+    ng = src.size
+    # rank of every record's row / column cut inside its group (scalar keys group * big + cut keep np.unique 1-D)
+    big = max(int(um[:, 6 + gn:].max()) + 1, 1)
+    rk, ri = np.unique(grp * big + r0, return_inverse=True)       # sorted (group, r0) pairs
+    ck, ci = np.unique(grp * big + c0, return_inverse=True)
+    rkey = np.stack([rk // big, rk % big], axis=1)
+    ckey = np.stack([ck // big, ck % big], axis=1)
+    nrs = np.bincount(rkey[:, 0], minlength=ng)
+    ncs = np.bincount(ckey[:, 0], minlength=ng)
+    rstart = np.concatenate(([0], np.cumsum(nrs)))[:-1]
+    cstart = np.concatenate(([0], np.cumsum(ncs)))[:-1]
+    ri = ri - rstart[grp]
+    ci = ci - cstart[grp]
+    if not np.array_equal(np.bincount(grp, minlength=ng), nrs * ncs):
+        raise ValueError("unmerge rectangles of a block do not form a grid")
+    dst_ptr = np.concatenate(([0], np.cumsum(nrs * ncs)))
+    dst = np.full(int(dst_ptr[-1]), -1, dtype=I64)
+    dst[dst_ptr[grp] + ri * ncs[grp] + ci] = sln0
+    # cuts: the sorted starts of a group followed by the extent of the merged block; rectangles must tile it
+    M_g = np.zeros(ng, dtype=I64); N_g = np.zeros(ng, dtype=I64)
+    M_g[grp], N_g[grp] = DoM, DoN
+    row_ptr = np.concatenate(([0], np.cumsum(nrs + 1)))
+    col_ptr = np.concatenate(([0], np.cumsum(ncs + 1)))
+    row_cuts = np.empty(int(row_ptr[-1]), dtype=I64)
+    col_cuts = np.empty(int(col_ptr[-1]), dtype=I64)
+    row_cuts[row_ptr[rkey[:, 0]] + (np.arange(rkey.shape[0]) - rstart[rkey[:, 0]])] = rkey[:, 1]
+    col_cuts[col_ptr[ckey[:, 0]] + (np.arange(ckey.shape[0]) - cstart[ckey[:, 0]])] = ckey[:, 1]
+    row_cuts[row_ptr[1:] - 1] = M_g
+    col_cuts[col_ptr[1:] - 1] = N_g
+    rnext = row_cuts[row_ptr[grp] + ri + 1]
+    cnext = col_cuts[col_ptr[grp] + ci + 1]
+    ok = (dst >= 0).all() and (rnext == r1).all() and (cnext == c1).all() \
+        and (row_cuts[row_ptr[:-1]] == 0).all() and (col_cuts[col_ptr[:-1]] == 0).all()
+    if not ok:
+        raise ValueError("unmerge rectangles do not tile the merged block")
+    # problems -> groups
+    slc0, Mp, Np = md[:, 0], md[:, 2], md[:, 3]
+    pos = np.searchsorted(src, slc0)
+    pos_c = np.minimum(pos, ng - 1)
+    hit = src[pos_c] == slc0
+    empty = (Mp * Np) == 0
+    if (~hit & ~empty).any():
+        raise ValueError("unmerge meta does not cover every block produced by dot")
+    scat_index = np.where(hit & ~empty, pos_c, -1).astype(I64)
+    live = scat_index >= 0
+    if np.unique(scat_index[live]).size != ng:
         raise ValueError("unmerge meta references blocks that dot does not produce")
-    f = lambda x: np.array(x, dtype=I64)
-    return scat_index, f(row_ptr), f(row_cuts), f(col_ptr), f(col_cuts), f(dst_ptr), f(dst)
+    if not (np.array_equal(M_g[scat_index[live]], Mp[live]) and np.array_equal(N_g[scat_index[live]], Np[live])):
+        raise ValueError("unmerge source shape differs from the dot block shape")
+    return scat_index, row_ptr.astype(I64), row_cuts, col_ptr.astype(I64), col_cuts, dst_ptr.astype(I64), dst
 
 
 def _matrix_view(Di, order, Dl, Dr):

@@ -27,7 +27,8 @@ from . import backend_b200 as _bk
 
 _HOT = _bk.HOT_FUNCTIONS
 _NATIVE = (torch.float64, torch.complex128)
-_state = {"module": None, "saved": None, "calls": {name: 0 for name in _HOT}, "delegated": {name: 0 for name in _HOT}}
+_state = {"module": None, "saved": None, "saved_f2m": None,
+          "calls": {name: 0 for name in _HOT + ("dot_unmerge",)}, "delegated": {name: 0 for name in _HOT}}
 
 
 def _stock():
@@ -87,8 +88,15 @@ def _make_hot(stock_fns, delegate):
         calls["transpose_dot_sum"] += 1
         return _bk.transpose_dot_sum(Adata, Bdata, meta_dot, Areshape, Breshape, Aorder, Border, Dsize)
 
+    def dot_unmerge(Adata, Bdata, meta_dot, Dsize, meta_unmerge):
+        """dot + unmerge in one launch; called by the fused fuse_to_matrix tensordot (enable_fused_tensordot)."""
+        if not _native(Adata, Bdata):
+            return unmerge(dot(Adata, Bdata, meta_dot, Dsize), meta_unmerge)
+        calls["dot_unmerge"] += 1
+        return _bk.dot_unmerge(Adata, Bdata, meta_dot, Dsize, meta_unmerge)
+
     return {"transpose_and_merge": transpose_and_merge, "unmerge": unmerge, "transpose": transpose, "dot": dot,
-            "transpose_dot_sum": transpose_dot_sum}
+            "transpose_dot_sum": transpose_dot_sum, "dot_unmerge": dot_unmerge}
 
 
 def module(delegate_other_dtypes=True):
@@ -127,6 +135,42 @@ def deactivate():
         for name, fn in _state["saved"].items():
             setattr(stock, name, fn)
         _state["saved"] = None
+
+
+def enable_fused_tensordot():
+    """Route YASTN's fuse_to_matrix tensordot through ``backend.dot_unmerge`` when the backend offers it: the grouped GEMM
+    writes straight into the unmerged block layout, i.e. 3 launches per tensordot instead of 4 and one pass less over the
+    result.  This is the optional 6-line change to ``_tensordot_f2m`` (yastn/tensor/_contractions.py:139-156) described in
+    INTEGRATION.md, applied from outside; backends without ``dot_unmerge`` keep the reference's call sequence."""
+    import yastn.tensor._contractions as C
+    from yastn.tensor._merging import _no_change_in_unmerge
+    if _state["saved_f2m"] is not None:
+        return
+    _state["saved_f2m"] = C._tensordot_f2m
+
+    def tensordot_f2m(a, b, nout_a, nin_a, nin_b, nout_b, s_c):
+        backend = a.config.backend
+        fused = getattr(backend, "dot_unmerge", None)
+        if fused is None:
+            return _state["saved_f2m"](a, b, nout_a, nin_a, nin_b, nout_b, s_c)
+        ind_a, ind_b = C._common_inds(a.struct.t, b.struct.t, nin_a, nin_b, a.ndim_n, b.ndim_n, a.config.sym.NSYM)
+        data_a, struct_a, slices_a, ls_l, ls_ac = C._merge_to_matrix(a, (nout_a, nin_a), ind_a)
+        data_b, struct_b, slices_b, ls_bc, ls_r = C._merge_to_matrix(b, (nin_b, nout_b), ind_b)
+        if ls_ac != ls_bc:
+            raise C.YastnError('Bond dimensions do not match.')
+        meta_dot, struct_m, slices_m = C._meta_tensordot_f2m(struct_a, slices_a, struct_b, slices_b)
+        meta_unmerge, struct_c, slices_c = C._meta_unmerge_matrix(a.config, struct_m, slices_m, ls_l, ls_r, s_c)
+        if _no_change_in_unmerge(meta_unmerge):       # result already in block layout: plain dot (reference fast path)
+            return backend.dot(data_a, data_b, meta_dot, struct_m.size), struct_c, slices_c
+        return fused(data_a, data_b, meta_dot, struct_m.size, meta_unmerge), struct_c, slices_c
+    C._tensordot_f2m = tensordot_f2m
+
+
+def disable_fused_tensordot():
+    if _state["saved_f2m"] is not None:
+        import yastn.tensor._contractions as C
+        C._tensordot_f2m = _state["saved_f2m"]
+        _state["saved_f2m"] = None
 
 
 def call_counts():
