@@ -17,6 +17,6 @@ echo "== ncu full: gemm"
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 6 -c 2 -f -o $OUT/${TAG}_gemm \
    python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --sizes 16384 > $OUT/${TAG}_ncu_gemm.log 2>&1
 echo "== ncu full: copy"
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:copy_kernel -s 18 -c 6 -f -o $OUT/${TAG}_copy \
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:copy_kernel -s 12 -c 4 -f -o $OUT/${TAG}_copy \
    python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --sizes 16384 > $OUT/${TAG}_ncu_copy.log 2>&1
 ls -la $OUT
