@@ -12,8 +12,9 @@ the whole sweep (every size x pattern: merge A, merge B, grouped GEMM, unmerge).
 the sizes that carry the FLOPs and the sweep cycles through >10 GB between reuses, so no explicit L2 flush is needed.
 
 value  = algorithmic GFLOP/s (sum over meta_dot of 2*M*K*N) with inputs resident in HBM, CUDA-event timed.
-e2e    = same metric through the backend API with HOST (pinned) operands: H2D of A and B, the four backend
-         calls, D2H of the result, every step.
+e2e    = same metric through the backend API with HOST (pinned) operands: H2D of A and B, the backend calls,
+         D2H of the result, every step; copies run on their own streams so that the transfers of neighbouring
+         contractions overlap the kernels (full-duplex PCIe).
 N > 1  = the charge sectors of every contraction are sharded FLOP-balanced over the ranks (no collective on
          the data path); value = total FLOPs / max-over-ranks time ("strong" scaling).
 """
@@ -275,18 +276,41 @@ def main():
         out_host = [torch.empty(w["stage"]["dot"]["Dsize"], dtype=tdt).pin_memory() for w in work]
         h2d = sum(a.numel() * a.element_size() + b.numel() * b.element_size() for a, b in host)
         d2h = sum(o.numel() * o.element_size() for o in out_host)
-        e2e_steps = max(1, min(args.steps, 3))
+        e2e_steps = max(1, min(args.steps, 5))
+        # three streams: H2D of the next contraction and D2H of the previous one overlap the kernels of the current one
+        # (PCIe is full duplex); every contraction still does H2D -> merge/merge/GEMM+unmerge -> D2H inside the timed region
+        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         def e2e_pass():
-            for w, (ha, hb), ho in zip(work, host, out_host):
-                A = ha.to(dev, non_blocking=True); B = hb.to(dev, non_blocking=True)
+            cur = torch.cuda.current_stream(dev)
+            for w, (ha, hb), ho in e2e_order:
+                with torch.cuda.stream(s_in):
+                    A = ha.to(dev, non_blocking=True); B = hb.to(dev, non_blocking=True)
+                    ready = torch.cuda.Event(); ready.record(s_in)
+                cur.wait_event(ready)
+                A.record_stream(cur); B.record_stream(cur)
                 C = contract(w, A, B)
-                ho.copy_(C, non_blocking=True)
+                done = torch.cuda.Event(); done.record(cur)
+                s_out.wait_event(done)
+                with torch.cuda.stream(s_out):
+                    ho.copy_(C, non_blocking=True)
+                C.record_stream(s_out)
+        # largest contraction first: its D2H (2 GB at D=16384) then overlaps the H2D and kernels of the others; consecutive
+        # steps are not joined (the copy streams are ordered by events only), the timed region ends when the last D2H lands
+        e2e_order = sorted(zip(work, host, out_host), key=lambda t: -t[2].numel())
+        def e2e_join():
+            cur = torch.cuda.current_stream(dev)
+            cur.wait_stream(s_in)
+            cur.wait_stream(s_out)
         e2e_pass()
+        e2e_join()
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
+        s_in.wait_stream(torch.cuda.current_stream(dev))
+        s_out.wait_stream(torch.cuda.current_stream(dev))
         for _ in range(e2e_steps):
             e2e_pass()
+        e2e_join()
         f1.record()
         barrier()
         e2e_ms = f0.elapsed_time(f1) / e2e_steps
@@ -301,6 +325,14 @@ def main():
                "ms_per_step": e2e_max}
 
     if rank == 0:
+        # DRAM bytes of the dominant launch from the committed ncu --set full capture (not measurable outside a profiler)
+        traffic = traffic_of = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["gemm"]
+            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+            traffic_of = f"{tr['launch']}; algorithmic bytes of that launch {tr['algorithmic_bytes']:.3e}; {tr['source']}"
+        except Exception:
+            pass
         ms_step = ms / args.steps
         gflops = total_flops / (ms_step * 1e-3) * 1e-9
         gemm_tflops = own_flops * args.steps / (gemm_ms * 1e-3) * 1e-12 if gemm_ms > 0 else 0.0
@@ -314,7 +346,7 @@ def main():
                            "sharding": "charge sectors FLOP-balanced over ranks, no collective" if world > 1 else "single GPU"},
                 "gpu_launches": n_launch,
                 "roofline": {"kernel": "yb::gemm_kernel (grouped DMMA.8x8x4 block GEMM)", "bound": "tensor", "achieved": gemm_tflops,
-                             "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": gemm_tflops / FP64_PEAK_TFLOPS, "traffic": None,
+                             "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": gemm_tflops / FP64_PEAK_TFLOPS, "traffic": traffic, "traffic_of": traffic_of,
                              "peak_source": "measured FP64 DMMA pipe peak, tools/microbench/fp64_pipes.cu (profiles/fp64_peaks_r01.json); cuBLAS DGEMM 8192^3 = 35.5",
                              "gemm_share_of_step": gemm_ms / ms if ms > 0 else None,
                              "epilogue": "fused unmerge scatter" if fuse else "plain store + separate unmerge launch"},

@@ -302,3 +302,88 @@ def test_fused_tensordot_path(device, dtype):
     (yastn.tensordot(A2, B, axes=(0, 0)).norm() ** 2).backward()
     g_plain = A2._data.grad.detach().cpu().numpy()
     assert np.linalg.norm(g_fused - g_plain) <= 1e-12 * np.linalg.norm(g_plain)
+
+
+@pytest.mark.parametrize("sym", ["dense", "U1", "Z2", "U1xU1"])
+def test_kernel_tensordot_bs_boundary(device, sym):
+    """The single-call boundary: YASTN's no_fusion tensordot hands raw block tables to ``backend.kernel_tensordot_bs``
+    when BACKEND_ID == 'torch_cpp' (yastn/tensor/_contractions.py:199-242; reference implementation
+    backend_torch_cpp.py:173-228 = cuTENSOR).  Structure bit-exact, data 1e-12 against the numpy backend; autograd too."""
+    ref = yastn.make_config(sym=sym, backend="np", tensordot_policy="no_fusion")
+    our = yastn.make_config(sym=sym, backend=yastn_backend.module(bs_boundary=True), tensordot_policy="no_fusion", default_device=device)
+    assert our.backend.BACKEND_ID == "torch_cpp" and yastn_backend.module().BACKEND_ID == "torch"
+    ref.backend.random_seed(29)
+    if sym == "dense":
+        a = yastn.rand(config=ref, s=(-1, 1, 1, -1), D=(2, 3, 4, 5))
+        b = yastn.rand(config=ref, s=(1, -1, 1), D=(2, 3, 5), dtype="complex128")
+        cases = [((0, 3), (0, 2)), ((1,), (1,))]
+    elif sym == "U1":
+        a, b = u1_operands(ref, "complex128")
+        cases = [((0, 1), (0, 1)), ((0,), (0,)), ((1, 0), (1, 0))]
+    elif sym == "Z2":
+        L = yastn.Leg(ref, s=1, t=(0, 1), D=(7, 9)); p = yastn.Leg(ref, s=1, t=(0, 1), D=(1, 1))
+        a = yastn.rand(ref, legs=[L.conj(), p, p, L], n=0)
+        b = yastn.rand(ref, legs=[L.conj(), p, L], n=1)
+        cases = [((3,), (0,))]
+    else:
+        L = yastn.gaussian_leg(ref, s=1, n=(0, 0), sigma=1.0, D_total=24, method="round")
+        p = yastn.Leg(ref, s=1, t=((0, 0), (1, 0), (0, 1), (1, 1)), D=(1, 1, 1, 1))
+        a = yastn.rand(ref, legs=[L.conj(), p, L], n=(0, 0), dtype="complex128")
+        b = yastn.rand(ref, legs=[L.conj(), p.conj(), p, L], n=(0, 0), dtype="complex128")
+        cases = [((2,), (0,)), ((1, 2), (1, 0))]
+    A, B = mirror(a, our), mirror(b, our)
+    n0 = yastn_backend.call_counts()["native"]["kernel_tensordot_bs"]
+    for axes in cases:
+        close(yastn.tensordot(A, B, axes=axes), yastn.tensordot(a, b, axes=axes))
+    # lazy transpose + conj of one operand reach the boundary as permuted native axes / a conj bit on the data
+    close(yastn.tensordot(A.transpose(tuple(range(A.ndim))[::-1]), B, axes=((A.ndim - 1 - cases[0][0][0],), (cases[0][1][0],))),
+          yastn.tensordot(a.transpose(tuple(range(a.ndim))[::-1]), b, axes=((a.ndim - 1 - cases[0][0][0],), (cases[0][1][0],))))
+    close(yastn.tensordot(A, A, axes=((0, 1), (0, 1)), conj=(0, 1)), yastn.tensordot(a, a, axes=((0, 1), (0, 1)), conj=(0, 1)))
+    assert yastn_backend.call_counts()["native"]["kernel_tensordot_bs"] - n0 >= len(cases) + 2
+    # gradients through the boundary against the stock torch backend
+    stock = yastn.make_config(sym=sym, backend="torch", tensordot_policy="no_fusion")
+    grads = []
+    if sym == "dense":      # the reference's own no_fusion backward does not promote mixed dtypes: same dtype on both sides
+        a = a.to(dtype="complex128")
+    for cfg in (stock, our):
+        x, y = mirror(a, cfg), mirror(b, cfg)
+        x.requires_grad_(True); y.requires_grad_(True)
+        (yastn.tensordot(x, y, axes=cases[0]).norm() ** 2).backward()
+        grads.append((x._data.grad.detach().cpu().numpy(), y._data.grad.detach().cpu().numpy()))
+    for g_ref, g in zip(grads[0], grads[1]):
+        assert np.linalg.norm(g - g_ref) <= 1e-11 * np.linalg.norm(g_ref)
+
+
+@pytest.mark.parametrize("sym", ["U1", "U1xU1"])
+def test_bs_to_tds_matches_reference_meta(sym):
+    """plans.bs_to_tds (the meta pass behind kernel_tensordot_bs) against the reference's own _meta_tensordot_nf
+    (yastn/tensor/_contractions.py:349-450) on the block tables YASTN would hand over: same result-block slices and
+    shapes, same reshape records, same set of block pairs per result block."""
+    from yastn.tensor._contractions import _meta_tensordot_nf, _common_inds
+    from yastn_b200 import plans
+    cfg = yastn.make_config(sym=sym, backend="np")
+    cfg.backend.random_seed(31)
+    if sym == "U1":
+        a, b = u1_operands(cfg, "float64")
+        nout_a, nin_a, nin_b, nout_b = (2, 3), (0, 1), (0, 1), (2,)
+    else:
+        L = yastn.gaussian_leg(cfg, s=1, n=(0, 0), sigma=1.5, D_total=40, method="round")
+        p = yastn.Leg(cfg, s=1, t=((0, 0), (1, 0), (0, 1), (1, 1)), D=(1, 2, 1, 1))
+        a = yastn.rand(cfg, legs=[L.conj(), p, L], n=(0, 0))
+        b = yastn.rand(cfg, legs=[L.conj(), p.conj(), p, L], n=(1, 0))
+        nout_a, nin_a, nin_b, nout_b = (1, 0), (2,), (0,), (3, 1, 2)
+    nsym = cfg.sym.NSYM
+    ind_a, ind_b = _common_inds(a.struct.t, b.struct.t, nin_a, nin_b, a.ndim_n, b.ndim_n, nsym)
+    meta_dot, reshape_a, reshape_b, struct_c, slices_c, _, _ = _meta_tensordot_nf(a.struct, a.slices, b.struct, b.slices, ind_a, ind_b,
+                                                                                  nout_a, nin_a, nin_b, nout_b)
+    at = a.struct.t if ind_a is None else tuple(a.struct.t[i] for i in ind_a)
+    asl = a.slices if ind_a is None else tuple(a.slices[i] for i in ind_a)
+    bt = b.struct.t if ind_b is None else tuple(b.struct.t[i] for i in ind_b)
+    bsl = b.slices if ind_b is None else tuple(b.slices[i] for i in ind_b)
+    md, ra, rb = plans.bs_to_tds(at, asl, nout_a, nin_a, bt, bsl, nout_b, nin_b, struct_c.t, slices_c)
+    assert ra == tuple((sl, tuple(D), int(l), int(r)) for sl, D, l, r in reshape_a)
+    assert rb == tuple((sl, tuple(D), int(l), int(r)) for sl, D, l, r in reshape_b)
+    assert len(md) == len(meta_dot)
+    for (sl, Dlr, pairs), (sl_r, Dlr_r, pairs_r) in zip(md, meta_dot):
+        assert sl == tuple(sl_r) and Dlr == tuple(int(x) for x in Dlr_r)
+        assert sorted(pairs) == sorted(tuple(p) for p in pairs_r)

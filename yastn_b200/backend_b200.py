@@ -33,6 +33,7 @@ _ITEMSIZE = {torch.float64: 8, torch.complex128: 16}
 
 def clear_plan_cache():
     _CACHE.clear()
+    _BS_CACHE.clear()
 
 
 def plan_cache_stats():
@@ -435,6 +436,39 @@ def transpose_dot_sum(Adata, Bdata, meta_dot, Areshape, Breshape, Aorder, Border
     if _needs_grad(Adata, Bdata):
         return _TransposeDotSum.apply(Adata, Bdata, meta_dot, Areshape, Breshape, Aorder, Border, Dsize)
     return _tds_forward(Adata, Bdata, meta_dot, Areshape, Breshape, Aorder, Border, Dsize)
+
+
+_BS_CACHE = plans.PlanCache(maxsize=1024)
+
+
+def kernel_tensordot_bs(a, b, NSYM, a_struct_t, a_slices, a_t_per_mode, a_D_per_mode, nout_a, nin_a,
+                        b_struct_t, b_slices, b_t_per_mode, b_D_per_mode, nout_b, nin_b,
+                        c_size, c_struct_t, c_slices, profile=False):
+    """Whole block-sparse contraction from raw block tables in one call: same signature and meaning as the reference's
+    single-call boundary (yastn/backend/backend_torch_cpp.py:173-228, reached from yastn/tensor/_contractions.py:199-242
+    when ``BACKEND_ID == 'torch_cpp'`` under the ``no_fusion`` policy; there it rebuilds a cuTENSOR plan on every call).
+    Here the block-pair join is a cached, vectorised meta pass (plans.bs_to_tds) and the contraction is ONE grouped-GEMM
+    launch (plus one packing copy per operand whose permuted blocks are not strided matrices).  The per-mode charge /
+    dimension lists are redundant with the ``D`` of the slice records and are not needed."""
+    _check(a, "kernel_tensordot_bs")
+    _check(b, "kernel_tensordot_bs")
+    if c_size == 0:
+        return torch.zeros(0, dtype=torch.promote_types(a.dtype, b.dtype), device=a.device)
+    a_struct_t, b_struct_t, c_struct_t = tuple(a_struct_t), tuple(b_struct_t), tuple(c_struct_t)
+    a_slices, b_slices, c_slices = tuple(a_slices), tuple(b_slices), tuple(c_slices)
+    nout_a, nin_a, nout_b, nin_b = tuple(nout_a), tuple(nin_a), tuple(nout_b), tuple(nin_b)
+    key = (a_struct_t, a_slices, nout_a, nin_a, b_struct_t, b_slices, nout_b, nin_b, c_struct_t, c_slices)
+    ent = _BS_CACHE._d.get(key)
+    if ent is None:
+        ent = (None, plans.bs_to_tds(a_struct_t, a_slices, nout_a, nin_a, b_struct_t, b_slices, nout_b, nin_b, c_struct_t, c_slices))
+        _BS_CACHE._d[key] = ent
+        _BS_CACHE.misses += 1
+        if len(_BS_CACHE._d) > _BS_CACHE.maxsize:
+            _BS_CACHE._d.popitem(last=False)
+    else:
+        _BS_CACHE.hits += 1
+    meta_dot, Areshape, Breshape = ent[1]
+    return transpose_dot_sum(a, b, meta_dot, Areshape, Breshape, nout_a + nin_a, nin_b + nout_b, c_size)
 
 
 HOT_FUNCTIONS = ("transpose_and_merge", "unmerge", "transpose", "dot", "transpose_dot_sum")

@@ -343,6 +343,83 @@ def pack_records(reshape, order):
     return transpose_records(order, meta)
 
 
+def bs_to_tds(a_t, a_slices, nout_a, nin_a, b_t, b_slices, nout_b, nin_b, c_t, c_slices):
+    """Raw block tables of ``kernel_tensordot_bs`` -> the metas of ``transpose_dot_sum``.
+
+    The single-call boundary (yastn/backend/backend_torch_cpp.py:173-188, called from yastn/tensor/_contractions.py:199-242)
+    hands over only the block lists: flattened charges ``*_t`` and ``_slc`` records (offset range, shape ``D``) of the blocks
+    of a and b that take part, the outgoing / contracted native axes, and the block list of the result.  Which blocks
+    multiply is decided here: a pair (ia, ib) contributes when its contracted-leg charges agree, and lands in the result
+    block whose charges are (outgoing charges of ia, outgoing charges of ib).  All joins are vectorised (sort-based), there
+    is no Python loop over block pairs.  Returns (meta_dot, Areshape, Breshape) in the layout of
+    yastn/tensor/_contractions.py:349-450.
+    """
+    na, nb, nc = len(a_t), len(b_t), len(c_t)
+    ra, rb = len(nout_a) + len(nin_a), len(nout_b) + len(nin_b)
+    if na == 0 or nb == 0 or nc == 0:
+        return (), (), ()
+    Da = np.array([s.D for s in a_slices], dtype=I64).reshape(na, ra)
+    Db = np.array([s.D for s in b_slices], dtype=I64).reshape(nb, rb)
+    w = len(a_t[0]) // ra                              # charges per leg (NSYM; 1 for the synthetic dense block)
+    ta = np.array(a_t, dtype=I64).reshape(na, ra, w)
+    tb = np.array(b_t, dtype=I64).reshape(nb, rb, w)
+    nout_a, nin_a, nout_b, nin_b = list(nout_a), list(nin_a), list(nout_b), list(nin_b)
+    ka = ta[:, nin_a, :].reshape(na, -1)
+    kb = tb[:, nin_b, :].reshape(nb, -1)
+    if ka.shape[1]:
+        _, inv = np.unique(np.vstack([ka, kb]), axis=0, return_inverse=True)
+        inv = inv.reshape(-1)
+    else:                                              # outer product: every pair matches
+        inv = np.zeros(na + nb, dtype=I64)
+    ida, idb = inv[:na], inv[na:]
+    nid = int(inv.max()) + 1
+    oa, ob = np.argsort(ida, kind="stable"), np.argsort(idb, kind="stable")
+    ca, cb = np.bincount(ida, minlength=nid), np.bincount(idb, minlength=nid)
+    sa = np.concatenate(([0], np.cumsum(ca)))[:-1]
+    sb = np.concatenate(([0], np.cumsum(cb)))[:-1]
+    cnt = ca * cb
+    first = np.concatenate(([0], np.cumsum(cnt)))[:-1]
+    pid = np.repeat(np.arange(nid), cnt)
+    pos = np.arange(int(cnt.sum())) - first[pid]
+    ia = oa[sa[pid] + pos // np.maximum(cb[pid], 1)]
+    ib = ob[sb[pid] + pos % np.maximum(cb[pid], 1)]
+    if (Da[ia][:, nin_a] != Db[ib][:, nin_b]).any():
+        raise ValueError("Bond dimensions do not match.")
+    # result block of every pair
+    tc = np.hstack([ta[ia][:, nout_a, :].reshape(ia.size, -1), tb[ib][:, nout_b, :].reshape(ib.size, -1)])
+    ctab = np.array(c_t, dtype=I64).reshape(nc, -1)
+    if ctab.shape[1]:
+        _, inv2 = np.unique(np.vstack([ctab, tc]), axis=0, return_inverse=True)
+        inv2 = inv2.reshape(-1)
+        lut = np.full(int(inv2.max()) + 1, -1, dtype=I64)
+        lut[inv2[:nc]] = np.arange(nc)
+        ic = lut[inv2[nc:]]
+    else:
+        ic = np.zeros(ia.size, dtype=I64)
+    if (ic < 0).any():
+        raise ValueError("kernel_tensordot_bs: a block pair has no result block in c_struct_t")
+    order = np.argsort(ic, kind="stable")
+    ia, ib, ic = ia[order], ib[order], ic[order]
+    Dal, Dar = Da[:, nout_a].prod(axis=1), Da[:, nin_a].prod(axis=1)
+    Dbl, Dbr = Db[:, nin_b].prod(axis=1), Db[:, nout_b].prod(axis=1)
+    Areshape = tuple((s.slcs[0], tuple(s.D), int(l), int(r)) for s, l, r in zip(a_slices, Dal, Dar))
+    Breshape = tuple((s.slcs[0], tuple(s.D), int(l), int(r)) for s, l, r in zip(b_slices, Dbl, Dbr))
+    bounds = np.searchsorted(ic, np.arange(nc + 1))
+    pairs = list(zip(ia.tolist(), ib.tolist()))
+    meta_dot = []
+    for k in range(nc):
+        lo, hi = int(bounds[k]), int(bounds[k + 1])
+        sl = c_slices[k].slcs[0]
+        if hi > lo:
+            Dl, Dr = int(Dal[ia[lo]]), int(Dbr[ib[lo]])
+        else:                                          # no contributing pair: the block is all zeros
+            Dl, Dr = sl[1] - sl[0], 1
+        if Dl * Dr != sl[1] - sl[0]:
+            raise ValueError("kernel_tensordot_bs: result block size differs from the product of the outgoing dimensions")
+        meta_dot.append((sl, (Dl, Dr), tuple(pairs[lo:hi])))
+    return tuple(meta_dot), Areshape, Breshape
+
+
 # -------------------------------------------------------------------------------------------------
 # device plans
 # -------------------------------------------------------------------------------------------------

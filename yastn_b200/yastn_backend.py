@@ -27,8 +27,8 @@ from . import backend_b200 as _bk
 
 _HOT = _bk.HOT_FUNCTIONS
 _NATIVE = (torch.float64, torch.complex128)
-_state = {"module": None, "saved": None, "saved_f2m": None,
-          "calls": {name: 0 for name in _HOT + ("dot_unmerge",)}, "delegated": {name: 0 for name in _HOT}}
+_state = {"module": {}, "saved": None, "saved_f2m": None,
+          "calls": {name: 0 for name in _HOT + ("dot_unmerge", "kernel_tensordot_bs")}, "delegated": {name: 0 for name in _HOT}}
 
 
 def _stock():
@@ -95,27 +95,39 @@ def _make_hot(stock_fns, delegate):
         calls["dot_unmerge"] += 1
         return _bk.dot_unmerge(Adata, Bdata, meta_dot, Dsize, meta_unmerge)
 
+    def kernel_tensordot_bs(a, b, *args, **kwargs):
+        """Single-call boundary of the reference's torch_cpp backend (yastn/backend/backend_torch_cpp.py:173-188)."""
+        if not _native(a, b):
+            raise TypeError("yastn_b200.kernel_tensordot_bs: float64 / complex128 CUDA tensors only")
+        calls["kernel_tensordot_bs"] += 1
+        return _bk.kernel_tensordot_bs(a, b, *args, **kwargs)
+
     return {"transpose_and_merge": transpose_and_merge, "unmerge": unmerge, "transpose": transpose, "dot": dot,
-            "transpose_dot_sum": transpose_dot_sum, "dot_unmerge": dot_unmerge}
+            "transpose_dot_sum": transpose_dot_sum, "dot_unmerge": dot_unmerge, "kernel_tensordot_bs": kernel_tensordot_bs}
 
 
-def module(delegate_other_dtypes=True):
-    """Backend module object for ``yastn.make_config(backend=...)`` (install mode A).  One instance per process:
-    ``_config`` is an lru_cache key inside YASTN, so the module identity must be stable."""
-    if _state["module"] is None:
+def module(delegate_other_dtypes=True, bs_boundary=False):
+    """Backend module object for ``yastn.make_config(backend=...)`` (install mode A).  One instance per variant and
+    process: ``_config`` is an lru_cache key inside YASTN, so the module identity must be stable.
+
+    ``bs_boundary=True`` returns the variant whose ``BACKEND_ID`` is ``"torch_cpp"``: YASTN then routes ``no_fusion``
+    contractions through the single-call ``kernel_tensordot_bs`` boundary (yastn/tensor/_contractions.py:199-242)."""
+    variant = bool(bs_boundary)
+    if variant not in _state["module"]:
         stock = _stock()
         saved = _state["saved"] or {n: getattr(stock, n) for n in _HOT}
-        mod = types.ModuleType("yastn_b200_backend", "stock yastn torch backend with the B200 contraction kernels")
+        mod = types.ModuleType("yastn_b200_backend" + ("_bs" if variant else ""),
+                               "stock yastn torch backend with the B200 contraction kernels")
         for name in dir(stock):
             if not name.startswith("__"):
                 setattr(mod, name, getattr(stock, name))
         for name, fn in _make_hot(saved, delegate_other_dtypes).items():
             setattr(mod, name, fn)
-        mod.BACKEND_ID = "torch"
+        mod.BACKEND_ID = "torch_cpp" if variant else "torch"
         mod.clear_plan_cache = _bk.clear_plan_cache
         mod.plan_cache_stats = _bk.plan_cache_stats
-        _state["module"] = mod
-    return _state["module"]
+        _state["module"][variant] = mod
+    return _state["module"][variant]
 
 
 def activate(delegate_other_dtypes=True):
