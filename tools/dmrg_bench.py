@@ -52,6 +52,38 @@ def build(model, N, cfg_kw, yastn, mps):
     return ops, I, H, n_total
 
 
+def profiled(backend, device, prof):
+    """Copy of the backend module whose public functions are timed (device-synchronised) into ``prof``."""
+    import importlib
+    import types
+    import torch
+    if isinstance(backend, str):
+        backend = importlib.import_module("yastn.backend.backend_" + backend)
+    mod = types.ModuleType("profiled_" + backend.__name__.split(".")[-1])
+    for name in dir(backend):
+        if not name.startswith("__"):
+            setattr(mod, name, getattr(backend, name))
+
+    def wrap(name, fn):
+        def f(*a, **k):
+            if device != "cpu":
+                torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            out = fn(*a, **k)
+            if device != "cpu":
+                torch.cuda.synchronize()
+            e = prof.setdefault(name, [0, 0.0])
+            e[0] += 1
+            e[1] += time.perf_counter() - t0
+            return out
+        return f
+    for name in list(vars(mod)):
+        fn = getattr(mod, name)
+        if isinstance(fn, types.FunctionType) and not name.startswith("_"):
+            setattr(mod, name, wrap(name, fn))
+    return mod
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--model", default="heisenberg")
@@ -63,6 +95,8 @@ def main():
     ap.add_argument("--dtype", default="float64")
     ap.add_argument("--policy", default="fuse_to_matrix")
     ap.add_argument("--out", default=None)
+    ap.add_argument("--D0", type=int, default=None, help="bond dimension of the random initial MPS (default min(D, 32))")
+    ap.add_argument("--shim", action="store_true", help="CPU table interpreter instead of the kernels (host-logic check, tests/cpu_shim.py)")
     ap.add_argument("--fused", action="store_true", help="b200 only: fuse dot+unmerge into one launch (yastn_backend.enable_fused_tensordot)")
     ap.add_argument("--profile", action="store_true", help="time every backend function (device-synchronised: perturbs the totals)")
     args = ap.parse_args()
@@ -75,6 +109,10 @@ def main():
     counts = None
     if args.backend == "b200":
         from yastn_b200 import yastn_backend
+        if args.shim:
+            import cpu_shim
+            cpu_shim.install()
+            args.device = "cpu"
         backend = yastn_backend.module()
         counts = yastn_backend.call_counts
         if args.fused:
@@ -84,38 +122,11 @@ def main():
     device = "cpu" if args.backend == "np" else args.device
     prof = {}
     if args.profile:
-        import types
-        import torch
-        if isinstance(backend, str):
-            import importlib
-            stock = importlib.import_module("yastn.backend.backend_" + backend)
-            mod = types.ModuleType("profiled_" + backend)
-            for name in dir(stock):
-                if not name.startswith("__"):
-                    setattr(mod, name, getattr(stock, name))
-            backend = mod
-
-        def wrap(name, fn):
-            def f(*a, **k):
-                if device != "cpu":
-                    torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                out = fn(*a, **k)
-                if device != "cpu":
-                    torch.cuda.synchronize()
-                e = prof.setdefault(name, [0, 0.0])
-                e[0] += 1
-                e[1] += time.perf_counter() - t0
-                return out
-            return f
-        for name in list(vars(backend)):
-            fn = getattr(backend, name)
-            if isinstance(fn, types.FunctionType) and not name.startswith("_"):
-                setattr(backend, name, wrap(name, fn))
+        backend = profiled(backend, device, prof)
     cfg_kw = dict(backend=backend, default_device=device, tensordot_policy=args.policy, default_dtype=args.dtype)
     ops, I, H, n_total = build(args.model, args.N, cfg_kw, yastn, mps)
     ops.random_seed(seed=0)
-    psi = mps.random_mps(I, n=n_total, D_total=min(args.D, 32), dtype=args.dtype)
+    psi = mps.random_mps(I, n=n_total, D_total=args.D0 or min(args.D, 32), dtype=args.dtype)
     sync = (lambda: None)
     if device != "cpu":
         import torch
