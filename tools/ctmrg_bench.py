@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--dtype", default="float64")
     ap.add_argument("--policy", default="fuse_to_matrix")
     ap.add_argument("--fused", action="store_true")
+    ap.add_argument("--decomp-workers", type=int, default=None, help="b200 only: sector streams of svd/qr/eigh (1 = the reference's serial loop)")
     ap.add_argument("--profile", action="store_true", help="time every backend function (device-synchronised: perturbs the totals)")
     ap.add_argument("--shim", action="store_true", help="CPU table interpreter instead of the kernels (host-logic check, tests/cpu_shim.py)")
     ap.add_argument("--out", default=None)
@@ -49,6 +50,9 @@ def main():
             cpu_shim.install()
             device = "cpu"
         backend = yastn_backend.module()
+        if args.decomp_workers is not None:
+            from yastn_b200 import decomp
+            decomp.set_workers(args.decomp_workers)
         counts = yastn_backend.call_counts
         if args.fused:
             yastn_backend.enable_fused_tensordot()
@@ -81,7 +85,7 @@ def main():
     chi_reached = max(max(env[(0, 0)].tl.get_shape()), max(env[(0, 0)].t.get_shape()))
     line = {"model": "ctmrg_U1", "D": args.D, "chi": args.chi, "chi_reached": int(chi_reached), "dtype": args.dtype,
             "backend": args.backend + ("+fused" if args.fused else "") + ("+shim" if args.shim else ""), "device": device,
-            "policy": args.policy, "sweep_s": times, "max_dsv": dsv, "hot_calls": counts() if counts else None}
+            "policy": args.policy, "sweep_s": times, "max_dsv": dsv, "hot_calls": counts() if counts else None, "decomp_workers": args.decomp_workers}
     if args.profile:
         top = sorted(prof.items(), key=lambda kv: -kv[1][1])[:16]
         line["backend_profile"] = {k: {"calls": v[0], "s": round(v[1], 3)} for k, v in top}

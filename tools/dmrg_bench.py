@@ -98,6 +98,7 @@ def main():
     ap.add_argument("--D0", type=int, default=None, help="bond dimension of the random initial MPS (default min(D, 32))")
     ap.add_argument("--shim", action="store_true", help="CPU table interpreter instead of the kernels (host-logic check, tests/cpu_shim.py)")
     ap.add_argument("--fused", action="store_true", help="b200 only: fuse dot+unmerge into one launch (yastn_backend.enable_fused_tensordot)")
+    ap.add_argument("--decomp-workers", type=int, default=None, help="b200 only: sector streams of svd/qr/eigh (1 = the reference's serial loop)")
     ap.add_argument("--profile", action="store_true", help="time every backend function (device-synchronised: perturbs the totals)")
     args = ap.parse_args()
     from yastn_loader import load_yastn
@@ -114,6 +115,9 @@ def main():
             cpu_shim.install()
             args.device = "cpu"
         backend = yastn_backend.module()
+        if args.decomp_workers is not None:
+            from yastn_b200 import decomp
+            decomp.set_workers(args.decomp_workers)
         counts = yastn_backend.call_counts
         if args.fused:
             yastn_backend.enable_fused_tensordot()
@@ -140,7 +144,7 @@ def main():
         energies.append(float(out.energy))
     line = {"model": args.model, "N": args.N, "D": args.D, "dtype": args.dtype, "backend": args.backend + ("+fused" if args.fused else ""), "device": device, "policy": args.policy,
             "sweep_s": times, "energy": energies, "bond_dims": max(psi.get_bond_dimensions()),
-            "hot_calls": counts() if counts else None}
+            "hot_calls": counts() if counts else None, "decomp_workers": args.decomp_workers}
     if args.profile:
         top = sorted(prof.items(), key=lambda kv: -kv[1][1])[:14]
         line["backend_profile"] = {k: {"calls": v[0], "s": round(v[1], 3)} for k, v in top}

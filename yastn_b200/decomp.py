@@ -1,0 +1,202 @@
+"""Sector-parallel matrix decompositions (the block loops of svd / svdvals / eigh / qr).
+
+The reference decomposes a block-sparse matrix with a Python loop over charge sectors, one cuSOLVER call per sector on
+the current stream and one host synchronisation per call (``info`` check):
+
+    svd      yastn/backend/_backend_torch_backwards.py:26-39  (SVDGESDD.forward, backend/linalg/torch_svd_gesdd.py:15-21,
+             ``torch.linalg.svd(A, full_matrices=..., driver='gesvd')`` on CUDA)
+    svdvals  yastn/backend/backend_torch.py:322-327
+    eigh     yastn/backend/backend_torch.py:365-380
+    qr       yastn/backend/backend_torch.py:475-484
+
+After the contraction kernels these loops are what a DMRG / CTMRG sweep waits for (72 % of a D=4096 Hubbard sweep,
+profiles/e2e_targets_r01.jsonl): a sector of a few hundred rows keeps a handful of SMs busy and the host blocks on every
+sector.  Sectors are independent, so here they are dealt — heaviest first — to a small pool of host threads, each
+owning a CUDA stream and (through torch's per-thread handle pool) its own cuSOLVER handle: the factorisations of
+different sectors overlap on the device and the per-sector host synchronisations overlap with each other.  Every sector
+is still factorised by the same library routine with the same arguments as in the reference, so the results are
+bit-identical to the reference loop on the same device; only the schedule changes.
+
+Inputs that require grad keep the reference's autograd implementations (the pool is a forward-only schedule), CPU
+tensors keep the reference's loop.
+"""
+import os
+import threading
+from concurrent.futures import ThreadPoolExecutor
+
+import torch
+
+_WORKERS = int(os.environ.get("YASTN_B200_DECOMP_WORKERS", "8"))
+_SVD_DRIVER = os.environ.get("YASTN_B200_SVD_DRIVER", "gesvd")   # the reference's choice on CUDA (torch_svd_gesdd.py:17)
+_MIN_SECTORS = 2          # a single sector has nothing to overlap with
+_pools = {}
+_pools_lock = threading.Lock()
+_stats = {"parallel_calls": 0, "sectors": 0, "serial_calls": 0}
+_THREADS_WITHOUT_STREAMS = False   # test hook: exercise the thread pool on CPU tensors (tests/test_decomp.py)
+
+
+class _Pool:
+    """Host threads with one CUDA stream each, per device."""
+
+    def __init__(self, device, workers):
+        self.device = device
+        self.workers = workers
+        self.tls = threading.local()
+        self.streams = []
+        self.lock = threading.Lock()
+        self.exe = ThreadPoolExecutor(max_workers=workers, thread_name_prefix=f"yb_decomp{device.index}")
+
+    def stream(self):
+        if self.device.type != "cuda":
+            return None
+        s = getattr(self.tls, "stream", None)
+        if s is None:
+            s = torch.cuda.Stream(self.device)
+            self.tls.stream = s
+            with self.lock:
+                self.streams.append(s)
+        return s
+
+
+def _pool(device):
+    with _pools_lock:
+        key = (device.type, device.index)
+        p = _pools.get(key)
+        if p is None or p.workers != _WORKERS:
+            p = _Pool(device, _WORKERS)
+            _pools[key] = p
+        return p
+
+
+def set_workers(n):
+    """Number of sector streams (1 = the reference's serial schedule)."""
+    global _WORKERS
+    _WORKERS = max(1, int(n))
+
+
+def stats():
+    return dict(_stats)
+
+
+def run_sectors(fn, recs, costs, device):
+    """Call ``fn(rec)`` for every record, concurrently over the sector pool of ``device`` (heaviest first, dynamic
+    dealing).  Returns when every call has been *issued* and the caller's current stream has been made to wait for all
+    of them, i.e. with torch's usual stream semantics for the caller."""
+    n = len(recs)
+    if n == 0:
+        return
+    cuda = device.type == "cuda"
+    if not (cuda or _THREADS_WITHOUT_STREAMS) or _WORKERS <= 1 or n < _MIN_SECTORS:
+        _stats["serial_calls"] += 1
+        for rec in recs:
+            fn(rec)
+        return
+    pool = _pool(device)
+    order = sorted(range(n), key=lambda i: -costs[i])
+    grad = torch.is_grad_enabled()
+    if cuda:
+        main = torch.cuda.current_stream(device)
+        start = torch.cuda.Event()
+        start.record(main)
+
+    def task(i):
+        if not cuda:
+            with torch.set_grad_enabled(grad):
+                return fn(recs[i])
+        s = pool.stream()
+        with torch.cuda.device(device), torch.cuda.stream(s), torch.set_grad_enabled(grad):
+            s.wait_event(start)
+            fn(recs[i])
+
+    futures = [pool.exe.submit(task, i) for i in order]
+    err = None
+    for f in futures:
+        try:
+            f.result()
+        except Exception as e:   # keep draining so that no worker is left writing into the outputs
+            err = err or e
+    if cuda:
+        with pool.lock:
+            streams = list(pool.streams)
+        for s in streams:
+            main.wait_stream(s)
+    _stats["parallel_calls"] += 1
+    _stats["sectors"] += n
+    if err is not None:
+        raise err
+
+
+def _svd_cost(D):
+    m, n = D
+    return m * n * min(m, n)
+
+
+def make(stock):
+    """The decomposition functions of a backend module, given the reference's own module ``stock`` (used for inputs that
+    require grad or live on the CPU)."""
+
+    def _defer(*tensors):
+        return any((not t.is_cuda) or (torch.is_grad_enabled() and t.requires_grad) for t in tensors)
+
+    def svd(data, meta, sizes, fullrank_uv=False, ad_decomp_reg=1.0e-12, diagnostics=None, **kwargs):
+        if _defer(data):
+            return stock.svd(data, meta, sizes, fullrank_uv=fullrank_uv, ad_decomp_reg=ad_decomp_reg, diagnostics=diagnostics, **kwargs)
+        real_dtype = data.real.dtype if data.is_complex() else data.dtype
+        Udata = torch.empty(sizes[0], dtype=data.dtype, device=data.device)
+        Sdata = torch.empty(sizes[1], dtype=real_dtype, device=data.device)
+        Vhdata = torch.empty(sizes[2], dtype=data.dtype, device=data.device)
+
+        def one(rec):
+            sl, D, slU, DU, slS, slV, DV = rec
+            U, S, Vh = torch.linalg.svd(data[sl[0]:sl[1]].view(D), full_matrices=fullrank_uv, driver=_SVD_DRIVER)
+            Udata[slU[0]:slU[1]].view(DU).copy_(U)
+            Sdata[slS[0]:slS[1]].copy_(S)
+            Vhdata[slV[0]:slV[1]].view(DV).copy_(Vh)
+        run_sectors(one, meta, [_svd_cost(m[1]) for m in meta], data.device)
+        return Udata, Sdata, Vhdata
+
+    def svdvals(data, meta, sizeS, **kwargs):
+        if _defer(data):
+            return stock.svdvals(data, meta, sizeS, **kwargs)
+        real_dtype = data.real.dtype if data.is_complex() else data.dtype
+        Sdata = torch.zeros((sizeS,), dtype=real_dtype, device=data.device)
+
+        def one(rec):
+            sl, D, slS = rec[0], rec[1], rec[4]
+            Sdata[slS[0]:slS[1]].copy_(torch.linalg.svdvals(data[sl[0]:sl[1]].view(D)))
+        run_sectors(one, meta, [_svd_cost(m[1]) for m in meta], data.device)
+        return Sdata
+
+    def eigh(data, meta=None, sizes=(1, 1), order_by_magnitude=False, ad_decomp_reg=1.0e-12):
+        if meta is None or order_by_magnitude or _defer(data):
+            return stock.eigh(data, meta, sizes, order_by_magnitude=order_by_magnitude, ad_decomp_reg=ad_decomp_reg)
+        real_dtype = data.real.dtype if data.is_complex() else data.dtype
+        Sdata = torch.zeros((sizes[0],), dtype=real_dtype, device=data.device)
+        Udata = torch.zeros((sizes[1],), dtype=data.dtype, device=data.device)
+
+        def one(rec):
+            sl, D, slU, DU, slS = rec
+            S, U = torch.linalg.eigh(data[sl[0]:sl[1]].view(D))
+            Sdata[slS[0]:slS[1]].copy_(S)
+            Udata[slU[0]:slU[1]].view(DU).copy_(U)
+        run_sectors(one, meta, [m[1][0] ** 3 for m in meta], data.device)
+        return Sdata, Udata
+
+    def qr(data, meta, sizes):
+        if _defer(data):
+            return stock.qr(data, meta, sizes)
+        Qdata = torch.zeros((sizes[0],), dtype=data.dtype, device=data.device)
+        Rdata = torch.zeros((sizes[1],), dtype=data.dtype, device=data.device)
+
+        def one(rec):
+            sl, D, slQ, DQ, slR, DR = rec
+            Q, R = torch.linalg.qr(data[sl[0]:sl[1]].view(D))
+            d = R.diagonal()
+            sR = torch.sign(d.real if d.is_complex() else d)
+            sR[sR == 0] = 1
+            Qdata[slQ[0]:slQ[1]].view(DQ).copy_(Q * sR)       # positive diagonal of R
+            Rdata[slR[0]:slR[1]].view(DR).copy_(sR.reshape([-1, 1]) * R)
+        run_sectors(one, meta, [_svd_cost(m[1]) for m in meta], data.device)
+        return Qdata, Rdata
+
+    return {"svd": svd, "svdvals": svdvals, "eigh": eigh, "qr": qr}

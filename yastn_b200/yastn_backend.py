@@ -24,10 +24,12 @@ import types
 import torch
 
 from . import backend_b200 as _bk
+from . import decomp as _decomp
 
 _HOT = _bk.HOT_FUNCTIONS
+_DECOMP = ("svd", "svdvals", "eigh", "qr")
 _NATIVE = (torch.float64, torch.complex128)
-_state = {"module": {}, "saved": None, "saved_f2m": None,
+_state = {"module": {}, "saved": None, "saved_f2m": None, "saved_decomp": None,
           "calls": {name: 0 for name in _HOT + ("dot_unmerge", "kernel_tensordot_bs")}, "delegated": {name: 0 for name in _HOT}}
 
 
@@ -106,6 +108,13 @@ def _make_hot(stock_fns, delegate):
             "transpose_dot_sum": transpose_dot_sum, "dot_unmerge": dot_unmerge, "kernel_tensordot_bs": kernel_tensordot_bs}
 
 
+def _make_decomp(stock):
+    """Sector-parallel svd / svdvals / eigh / qr (yastn_b200.decomp) on top of the reference's own implementations."""
+    if _state["saved_decomp"] is None:
+        _state["saved_decomp"] = types.SimpleNamespace(**{n: getattr(stock, n) for n in _DECOMP})
+    return _decomp.make(_state["saved_decomp"])
+
+
 def module(delegate_other_dtypes=True, bs_boundary=False):
     """Backend module object for ``yastn.make_config(backend=...)`` (install mode A).  One instance per variant and
     process: ``_config`` is an lru_cache key inside YASTN, so the module identity must be stable.
@@ -123,6 +132,8 @@ def module(delegate_other_dtypes=True, bs_boundary=False):
                 setattr(mod, name, getattr(stock, name))
         for name, fn in _make_hot(saved, delegate_other_dtypes).items():
             setattr(mod, name, fn)
+        for name, fn in _make_decomp(stock).items():
+            setattr(mod, name, fn)
         mod.BACKEND_ID = "torch_cpp" if variant else "torch"
         mod.clear_plan_cache = _bk.clear_plan_cache
         mod.plan_cache_stats = _bk.plan_cache_stats
@@ -137,6 +148,8 @@ def activate(delegate_other_dtypes=True):
         _state["saved"] = {n: getattr(stock, n) for n in _HOT}
     for name, fn in _make_hot(_state["saved"], delegate_other_dtypes).items():
         setattr(stock, name, fn)
+    for name, fn in _make_decomp(stock).items():
+        setattr(stock, name, fn)
     return stock
 
 
@@ -147,6 +160,9 @@ def deactivate():
         for name, fn in _state["saved"].items():
             setattr(stock, name, fn)
         _state["saved"] = None
+        if _state["saved_decomp"] is not None:
+            for name in _DECOMP:
+                setattr(stock, name, getattr(_state["saved_decomp"], name))
 
 
 def enable_fused_tensordot():
