@@ -101,6 +101,19 @@ int yb_match_sectors(const int64_t* a_key, const int64_t* a_dims, const int64_t*
                      const int64_t* b_key, const int64_t* b_dims, const int64_t* b_off, int64_t nb, int key_width,
                      int64_t capacity, int64_t* problems, int64_t* segments, int64_t* result, int64_t* scratch, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Peer arenas (multi-GPU, one process per GPU on one box).  The reference has no multi-GPU path for a
+ * single contraction (its only multi-process code farms whole CTM environments out, yastn/tn/fpeps/envs/_env_ctm_dist_mp.py);
+ * these calls give the block exchange between sharded contractions a direct NVLink data path: yb_peer_alloc creates a device
+ * buffer and its 64-byte CUDA IPC handle, yb_peer_open maps another rank's buffer into this process.  A copy plan whose
+ * records use  dst_base = (peer_ptr - local_ptr) / itemsize + offset  (int64 element offsets are unrestricted), or a GEMM
+ * scatter table whose destinations are shifted the same way, then writes blocks straight into the peer's HBM.
+ * ---------------------------------------------------------------------------------------------- */
+int yb_peer_alloc(int64_t bytes, int device, void** ptr, unsigned char handle[64]);
+int yb_peer_open(const unsigned char handle[64], int device, void** ptr);
+int yb_peer_close(void* ptr);
+int yb_peer_free(void* ptr);
+
 #ifdef __cplusplus
 }
 #endif

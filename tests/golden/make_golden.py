@@ -290,6 +290,33 @@ def bench_structs():
     print("structs_bench:", len(cases), "cases,", os.path.getsize(os.path.join(HERE, "structs_bench.json.gz")), "bytes")
 
 
+def chain_structs():
+    """Two consecutive contractions that group the shared tensor by DIFFERENT legs (multi-GPU redistribution fixture,
+    SURVEY 8e): step 1  C = tensordot(A, F, (3, 0)) shards by the charge of A's right leg, step 2  E = tensordot(G, C, (2, 0))
+    shards by the charge of C's left leg, so the blocks of C change owner between the two."""
+    cases = {}
+    for sigma, D in ((1.0, 1024), (2.5, 4096)):
+        cfg = yastn.make_config(sym='U1', backend='np')
+        L = yastn.gaussian_leg(cfg, s=1, n=0, sigma=sigma, D_total=D, method='round')
+        p = yastn.Leg(cfg, s=1, t=(-1, 1), D=(1, 1))
+        w = yastn.Leg(cfg, s=1, t=(-2, 0, 2), D=(1, 3, 1))
+        A = yastn.zeros(cfg, legs=[L.conj(), p, p, L], n=0)
+        F = yastn.zeros(cfg, legs=[L.conj(), w, L], n=0)
+        G = yastn.zeros(cfg, legs=[L.conj(), w, L], n=0)
+        C = yastn.tensordot(A, F, axes=(3, 0))
+        cases[f"U1_D{D}_chain"] = {"step1": _record_tensordot(A, F, (3, 0), ("fuse_to_matrix",)),
+                                   "step2": _record_tensordot(G, C, (2, 0), ("fuse_to_matrix",))}
+        print("chain", D, "C blocks", len(C.struct.t), "size", C.size)
+    with gzip.open(os.path.join(HERE, "structs_chain.json.gz"), "wt") as f:
+        json.dump(cases, f, separators=(",", ":"))
+    print("structs_chain:", os.path.getsize(os.path.join(HERE, "structs_chain.json.gz")), "bytes")
+
+
 if __name__ == "__main__":
-    make_small()
-    bench_structs()
+    import sys
+    if "--chain-only" in sys.argv:
+        chain_structs()
+    else:
+        make_small()
+        bench_structs()
+        chain_structs()

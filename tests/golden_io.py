@@ -46,3 +46,17 @@ def bench_structs():
             return tup(d)
         _cache["bench"] = {k: conv(v) for k, v in raw.items()}
     return _cache["bench"]
+
+
+def chain_structs():
+    """Dict name -> {"step1", "step2"}: two consecutive contractions grouping the shared tensor by different legs."""
+    if "chain" not in _cache:
+        with gzip.open(os.path.join(GOLDEN, "structs_chain.json.gz"), "rt") as f:
+            raw = json.load(f)
+
+        def conv(d):
+            if isinstance(d, dict):
+                return {k: conv(v) for k, v in d.items()}
+            return tup(d)
+        _cache["chain"] = {k: conv(v) for k, v in raw.items()}
+    return _cache["chain"]

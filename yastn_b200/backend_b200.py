@@ -260,17 +260,20 @@ class _DotUnmerge(torch.autograd.Function):
     (reference: the two calls at yastn/tensor/_contractions.py:152-155).  Backward = adjoint unmerge + dot backward."""
 
     @staticmethod
-    def forward(Adata, Bdata, meta_dot, Dsize, meta_unmerge):
+    def forward(Adata, Bdata, meta_dot, Dsize, meta_unmerge, out=None, dst_shift=None):
         Adata, Bdata, dtype = _promote(Adata, Bdata)
         dev = Adata.device.index
-        key = ("dotunm", id(meta_dot), id(meta_unmerge), dtype, dev)
+        key = ("dotunm", id(meta_dot), id(meta_unmerge), id(dst_shift), dtype, dev)
 
         def build():
             problems, segments = plans.dot_tables(meta_dot)
-            scatter = plans.unmerge_scatter_tables(meta_dot, meta_unmerge)
-            return {"fwd": plans.GemmPlan(problems, segments, _DTYPE_CODE[dtype], dev, scatter), "ref": meta_unmerge}
+            scatter = plans.unmerge_scatter_tables(meta_dot, meta_unmerge, dst_shift)
+            return {"fwd": plans.GemmPlan(problems, segments, _DTYPE_CODE[dtype], dev, scatter), "ref": (meta_unmerge, dst_shift)}
         ent = _CACHE.get(key, meta_dot, build)
-        out = torch.empty(Dsize, dtype=dtype, device=Adata.device)
+        if out is None:
+            out = torch.empty(Dsize, dtype=dtype, device=Adata.device)
+        elif out.dtype != dtype or out.numel() != Dsize or out.device != Adata.device or not out.is_contiguous():
+            raise ValueError("yastn_b200.dot_unmerge: out must be a contiguous 1-D tensor of the result's dtype, size and device")
         _run_gemm(ent["fwd"], Adata, Bdata, out)
         return out
 
@@ -421,13 +424,20 @@ def dot(Adata, Bdata, meta_dot, Dsize):
     return _Dot.forward(Adata, Bdata, meta_dot, Dsize)
 
 
-def dot_unmerge(Adata, Bdata, meta_dot, Dsize, meta_unmerge):
-    """``unmerge(dot(Adata, Bdata, meta_dot, Dsize), meta_unmerge)`` in one launch (fused scatter epilogue)."""
+def dot_unmerge(Adata, Bdata, meta_dot, Dsize, meta_unmerge, out=None, dst_shift=None):
+    """``unmerge(dot(Adata, Bdata, meta_dot, Dsize), meta_unmerge)`` in one launch (fused scatter epilogue).
+
+    Multi-GPU (forward only): ``out`` is the result buffer inside a ``peer.PeerArena`` and ``dst_shift`` an int64 array with
+    one entry per record of ``meta_unmerge`` — the element offset (``PeerArena.shift``) of the rank that multiplies that
+    output block next, 0 for this rank.  The epilogue then stores every block straight into its next owner's HBM over
+    NVLink while the remaining tiles are still being multiplied: GEMM, unmerge and redistribution in one launch."""
     _check(Adata, "dot_unmerge")
     _check(Bdata, "dot_unmerge")
     if _needs_grad(Adata, Bdata):
+        if out is not None or dst_shift is not None:
+            raise ValueError("yastn_b200.dot_unmerge: out= / dst_shift= are forward-only")
         return _DotUnmerge.apply(Adata, Bdata, meta_dot, Dsize, meta_unmerge)
-    return _DotUnmerge.forward(Adata, Bdata, meta_dot, Dsize, meta_unmerge)
+    return _DotUnmerge.forward(Adata, Bdata, meta_dot, Dsize, meta_unmerge, out, dst_shift)
 
 
 def transpose_dot_sum(Adata, Bdata, meta_dot, Areshape, Breshape, Aorder, Border, Dsize):

@@ -58,11 +58,24 @@ class _Pool:
         return s
 
 
+def _warm_linalg(device):
+    """torch loads its CUDA linalg library lazily on the first linalg call and that first call must not race with another
+    one ("lazy wrapper should be called at most once"): make it here, on the caller's thread, before any worker runs."""
+    x = torch.eye(2, dtype=torch.float64, device=device)
+    torch.linalg.svd(x, full_matrices=False, driver=_SVD_DRIVER)
+    torch.linalg.svdvals(x)
+    torch.linalg.eigh(x)
+    torch.linalg.qr(x)
+    torch.cuda.synchronize(device)
+
+
 def _pool(device):
     with _pools_lock:
         key = (device.type, device.index)
         p = _pools.get(key)
         if p is None or p.workers != _WORKERS:
+            if p is None and device.type == "cuda":
+                _warm_linalg(device)
             p = _Pool(device, _WORKERS)
             _pools[key] = p
         return p

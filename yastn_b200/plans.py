@@ -204,13 +204,15 @@ def dot_backward_tables(meta_dot):
     return f(probA, 6), f(segA, 7), f(probB, 6), f(segB, 7)
 
 
-def unmerge_scatter_tables(meta_dot, meta_unmerge):
+def unmerge_scatter_tables(meta_dot, meta_unmerge, dst_shift=None):
     """Tables of the fused unmerge epilogue (include/yastn_b200.h, yb_gemm_plan_create_scatter).
 
     ``meta_unmerge`` (yastn/tensor/_merging.py:528-549) lists, for every merged C block ``slo`` of shape ``Do``,
     the rectangles ``((r0, r1), (c0, c1))`` that become the output blocks at ``sln``.  The rectangles of one merged
     block form a complete grid (row cuts x col cuts); the GEMM epilogue then writes every element straight to its
-    output block.  Returns (scat_index[nprob], row_ptr, row_cuts, col_ptr, col_cuts, dst_ptr, dst).
+    output block.  ``dst_shift`` (one int64 per record of ``meta_unmerge``) is added to the destination offset of that
+    output block: with peer arenas it redirects the block into another rank's buffer (peer.PeerArena.shift).
+    Returns (scat_index[nprob], row_ptr, row_cuts, col_ptr, col_cuts, dst_ptr, dst).
     """
     nprob, n = len(meta_dot), len(meta_unmerge)
     if n == 0:
@@ -244,7 +246,9 @@ def unmerge_scatter_tables(meta_dot, meta_unmerge):
         raise ValueError("unmerge rectangles of a block do not form a grid")
     dst_ptr = np.concatenate(([0], np.cumsum(nrs * ncs)))
     dst = np.full(int(dst_ptr[-1]), -1, dtype=I64)
-    dst[dst_ptr[grp] + ri * ncs[grp] + ci] = sln0
+    placed = np.zeros(dst.size, dtype=bool)
+    placed[dst_ptr[grp] + ri * ncs[grp] + ci] = True
+    dst[dst_ptr[grp] + ri * ncs[grp] + ci] = sln0 if dst_shift is None else sln0 + np.asarray(dst_shift, dtype=I64)
     # cuts: the sorted starts of a group followed by the extent of the merged block; rectangles must tile it
     M_g = np.zeros(ng, dtype=I64); N_g = np.zeros(ng, dtype=I64)
     M_g[grp], N_g[grp] = DoM, DoN
@@ -258,7 +262,7 @@ def unmerge_scatter_tables(meta_dot, meta_unmerge):
     col_cuts[col_ptr[1:] - 1] = N_g
     rnext = row_cuts[row_ptr[grp] + ri + 1]
     cnext = col_cuts[col_ptr[grp] + ci + 1]
-    ok = (dst >= 0).all() and (rnext == r1).all() and (cnext == c1).all() \
+    ok = placed.all() and (rnext == r1).all() and (cnext == c1).all() \
         and (row_cuts[row_ptr[:-1]] == 0).all() and (col_cuts[col_ptr[:-1]] == 0).all()
     if not ok:
         raise ValueError("unmerge rectangles do not tile the merged block")

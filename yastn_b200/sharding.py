@@ -197,3 +197,101 @@ def gather_blocks(data, slices, owner, group=None):
             data[lo:hi] = buf[pos:pos + hi - lo]
             pos += hi - lo
     return data
+
+
+# -------------------------------------------------------------------------------------------------
+# block ownership of operands / results of a sector-sharded contraction, and the peer-memory exchange
+# -------------------------------------------------------------------------------------------------
+
+def operand_block_owner(stage, owner, which):
+    """Owner rank of every block of operand ``which`` ('a' or 'b') of a fuse_to_matrix contraction whose sectors are owned
+    according to ``owner`` (one rank per record of meta_dot).  Keys are the block slices (lo, hi) in the operand's own
+    storage: through ``meta_mrg`` every source block feeds exactly one merged block, and a merged block belongs to the
+    sector that multiplies it.  Blocks that take part in no product are absent."""
+    pos = 2 if which == "a" else 4
+    merged = {rec[pos]: o for rec, o in zip(stage["dot"]["meta_dot"], owner)}
+    m = stage["merge_" + which]
+    if m is None:
+        return merged
+    of_charge = {tn: merged[sln] for (tn, Dn, sln) in m["meta_new"] if sln in merged}
+    return {rec[1]: of_charge[rec[0]] for rec in m["meta_mrg"] if rec[0] in of_charge}
+
+
+def result_block_owner(stage, owner):
+    """Owner rank of every block of the result ({slice in the result's storage: rank})."""
+    merged = {rec[0]: o for rec, o in zip(stage["dot"]["meta_dot"], owner)}
+    if stage["unmerge"] is None:
+        return merged
+    return {rec[0]: merged[rec[2]] for rec in stage["unmerge"]["meta"]}
+
+
+def push_records(slices, owner_old, owner_new, rank, shifts):
+    """Copy records ([src_base, dst_base, extent, 1, 1], yb_copy_plan_create with rank 1) that move every block this rank
+    owns to its new owner: ``shifts[r]`` is the element offset turning a local address into rank r's (PeerArena.shift; 0 for
+    the rank itself).  ``owner_new`` entries may be a rank, a list of ranks (block needed by several) or None."""
+    import numpy as np
+    rows = []
+    for sl, o_old, o_new in zip(slices, owner_old, owner_new):
+        if o_old != rank or o_new is None:
+            continue
+        for dest in (o_new if isinstance(o_new, (list, tuple)) else (o_new,)):
+            if dest != rank and sl[1] > sl[0]:
+                rows.append((sl[0], sl[0] + shifts[dest], sl[1] - sl[0], 1, 1))
+    return np.array(rows, dtype=np.int64).reshape(len(rows), 5)
+
+
+class PeerExchange:
+    """All-to-all-v of whole blocks as ONE launch of the block-copy kernel over NVLink peer memory.
+
+    ``data`` must be carved out of a ``peer.PeerArena`` (same offset on every rank).  Every rank stores the blocks it owns
+    and another rank needs straight into that rank's copy of the buffer; ``arena.publish()`` afterwards makes them visible.
+    Replaces the per-block ``torch.cat`` / send / recv / copy-back of :func:`redistribute_blocks` (which remains the
+    NCCL / gloo path for buffers outside an arena)."""
+
+    def __init__(self, arena, data, slices, owner_old, owner_new):
+        from . import plans
+        if not arena.contains(data):
+            raise ValueError("PeerExchange: data does not live in the peer arena")
+        isz = data.element_size()
+        shifts = [0 if r == arena.rank else arena.shift(r, isz) for r in range(arena.world)]
+        self.recs = push_records(slices, owner_old, owner_new, arena.rank, shifts)
+        self.elements = int(self.recs[:, 2].sum()) if len(self.recs) else 0
+        self.arena = arena
+        self.plan = plans.CopyPlan(self.recs, 1, isz, data.device.index) if len(self.recs) else None
+
+    def run(self, data, publish=True):
+        import ctypes
+        import torch
+        if self.plan is not None:
+            st = ctypes.c_void_p(torch.cuda.current_stream(data.device).cuda_stream)
+            self.plan.run(data.data_ptr(), data.data_ptr(), data.numel(), 0, st)
+        if publish:
+            self.arena.publish()
+        return data
+
+
+def chain_ownership(stage1, stage2, world, operand="b"):
+    """Ownership of the blocks of the tensor that contraction 1 produces and contraction 2 consumes as ``operand``.
+
+    Both contractions are sharded by whole charge sectors (LPT).  Returns (owner1, owner2, slices, produced_by, needed_by):
+    the sector owners of both contractions, the block slices of the shared tensor in storage order, the rank that produces
+    each block and the rank that multiplies it next (None: the block takes part in no product of contraction 2)."""
+    owner1 = assign_sectors(stage1["dot"]["meta_dot"], world)
+    owner2 = assign_sectors(stage2["dot"]["meta_dot"], world)
+    produced = result_block_owner(stage1, owner1)
+    needed = operand_block_owner(stage2, owner2, operand)
+    slices = sorted(produced)
+    return owner1, owner2, slices, [produced[s] for s in slices], [needed.get(s) for s in slices]
+
+
+def unmerge_dst_shift(shard_stage, slices, needed_by, rank, shifts):
+    """``dst_shift`` of backend_b200.dot_unmerge for a sharded contraction: one element offset per record of the shard's
+    unmerge meta, sending every produced block to the rank that needs it next (0 = stays here)."""
+    import numpy as np
+    nxt = dict(zip(slices, needed_by))
+    out = np.zeros(len(shard_stage["unmerge"]["meta"]), dtype=np.int64)
+    for k, rec in enumerate(shard_stage["unmerge"]["meta"]):
+        dest = nxt.get(rec[0])
+        if dest is not None and dest != rank:
+            out[k] = shifts[dest]
+    return out
