@@ -312,11 +312,32 @@ def chain_structs():
     print("structs_chain:", os.path.getsize(os.path.join(HERE, "structs_chain.json.gz")), "bytes")
 
 
+def transpose_structs():
+    """Contractions whose merge is a genuine transposition of large blocks (copy-kernel tiled path at scale):
+    T1 = tensordot(A, conj(F), axes=(0, 0)) merges A[l*,p,p,r] as (p p r) x l, i.e. every (Dl x Dr) block is transposed."""
+    cases = {}
+    for sigma, D in ((2.5, 4096), (6.0, 16384)):
+        cfg = yastn.make_config(sym='U1', backend='np')
+        L = yastn.gaussian_leg(cfg, s=1, n=0, sigma=sigma, D_total=D, method='round')
+        p = yastn.Leg(cfg, s=1, t=(-1, 1), D=(1, 1))
+        w = yastn.Leg(cfg, s=1, t=(-2, 0, 2), D=(1, 3, 1))
+        A = yastn.zeros(cfg, legs=[L.conj(), p, p, L], n=0)
+        F = yastn.zeros(cfg, legs=[L.conj(), w, L], n=0)
+        cases[f"U1_D{D}_T1"] = _record_tensordot(A, F.conj(), (0, 0), ("fuse_to_matrix",))
+        print("transpose", D, "order", cases[f"U1_D{D}_T1"]["f2m"]["merge_a"]["order"])
+    with gzip.open(os.path.join(HERE, "structs_transpose.json.gz"), "wt") as f:
+        json.dump(cases, f, separators=(",", ":"))
+    print("structs_transpose:", os.path.getsize(os.path.join(HERE, "structs_transpose.json.gz")), "bytes")
+
+
 if __name__ == "__main__":
     import sys
-    if "--chain-only" in sys.argv:
+    if "--transpose-only" in sys.argv:
+        transpose_structs()
+    elif "--chain-only" in sys.argv:
         chain_structs()
     else:
         make_small()
         bench_structs()
         chain_structs()
+        transpose_structs()

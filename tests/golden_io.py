@@ -39,6 +39,10 @@ def bench_structs():
     if "bench" not in _cache:
         with gzip.open(os.path.join(GOLDEN, "structs_bench.json.gz"), "rt") as f:
             raw = json.load(f)
+        extra = os.path.join(GOLDEN, "structs_transpose.json.gz")      # T1 cases: merges that transpose large blocks
+        if os.path.exists(extra):
+            with gzip.open(extra, "rt") as f:
+                raw.update(json.load(f))
 
         def conv(d):
             if isinstance(d, dict):
@@ -60,3 +64,19 @@ def chain_structs():
             return tup(d)
         _cache["chain"] = {k: conv(v) for k, v in raw.items()}
     return _cache["chain"]
+
+
+def ref_merge_fixtures():
+    """The reference's own captured transpose_and_merge argument sets (experimental/main_d7chi98_1d.py) + output hashes."""
+    if "refmerge" not in _cache:
+        with gzip.open(os.path.join(GOLDEN, "ref_merge_fixtures.json.gz"), "rt") as f:
+            raw = json.load(f)
+        _cache["refmerge"] = {k: {x: tup(y) for x, y in v.items()} for k, v in raw.items()}
+    return _cache["refmerge"]
+
+
+def closed_form_input(n, dtype="float64"):
+    """data[i] = ((i * 2654435761) mod 2^32) / 2^32 (imaginary part: the same sequence reversed), as in make_ref_fixtures.py."""
+    i = np.arange(n, dtype=np.uint64)
+    x = ((i * np.uint64(2654435761)) % np.uint64(2 ** 32)).astype(np.float64) / 2.0 ** 32
+    return x + 1j * x[::-1] if dtype == "complex128" else x

@@ -148,7 +148,7 @@ def _run_f2m(bk, A, B, case):
 
 
 @pytest.mark.parametrize("name", ["U1_D64_P1", "U1_D64_P2", "U1_D64_P3", "U1_D1024_P1", "U1_D1024_P2", "U1_D1024_P3",
-                                  "Z2_D512_P1", "Z2_D512_P2", "U1_D2048_P2", "U1xU1_D4096_P1", "U1xU1_D4096_P2"])
+                                  "Z2_D512_P1", "Z2_D512_P2", "U1_D2048_P2", "U1xU1_D4096_P1", "U1xU1_D4096_P2", "U1_D4096_T1"])
 @pytest.mark.parametrize("dtype", ["float64", "complex128"])
 def test_tensordot_pipeline_vs_oracle(bk, name, dtype):
     """merge -> dot -> unmerge on benchmark-shaped structures (reference metas) against the CPU oracle."""
@@ -184,7 +184,27 @@ def test_policies_agree_on_gpu(bk, name):
     assert _relerr(out, ref) <= TOL
 
 
-@pytest.mark.parametrize("name", ["U1_D8192_P1", "U1_D16384_P2"])
+@pytest.mark.parametrize("dtype", ["float64", "complex128"])
+@pytest.mark.parametrize("name", ["U1_D4096_T1", "U1_D4096_P3", "U1xU1_D4096_P1"])
+def test_large_merges_bit_exact(bk, name, dtype):
+    """Both merges of benchmark-sized contractions against the oracle, bit for bit: T1 transposes every (Dl x Dr) block
+    (tiled path with ragged edge slabs), P3 interleaves two source blocks element-wise in the destination, U1xU1 is made
+    of thousands of small blocks (pack path)."""
+    case = bench_structs()[name]
+    rng = np.random.default_rng(4)
+    for key, n in (("merge_a", case["a"]["size"]), ("merge_b", case["b"]["size"])):
+        m = case["f2m"][key]
+        if m is None:
+            continue
+        X = rng.uniform(-1, 1, n)
+        if dtype == "complex128":
+            X = X + 1j * rng.uniform(-1, 1, n)
+        ref = orc.transpose_and_merge(X, m["order"], m["meta_new"], m["meta_mrg"], m["Dsize"])
+        got = bk.transpose_and_merge(_dev(X), m["order"], m["meta_new"], m["meta_mrg"], m["Dsize"])
+        assert np.array_equal(got.cpu().numpy(), ref), (name, key)
+
+
+@pytest.mark.parametrize("name", ["U1_D8192_P1", "U1_D16384_P2", "U1_D16384_T1"])
 def test_full_size_linearity_and_roundtrip(bk, name):
     """Full benchmark sizes (oracle too slow): size-independent properties.
     (1) merge followed by its adjoint restores every block that took part; (2) the contraction is linear in A."""

@@ -142,3 +142,29 @@ def test_unmerge_scatter_tables():
         ref = orc.unmerge(orc.dot(A, B, md, st["dot"]["Dsize"]), um)
         out = exec_gemm(problems, segments, A, B, np.full(st["dot"]["Dsize"], np.nan), scatter=scatter)
         assert np.linalg.norm(out - ref) <= 1e-13 * np.linalg.norm(ref)
+
+
+def test_fused_dot_unmerge_autograd_matches_two_calls_shim():
+    """Host wiring of the fused call under autograd (CPU table interpreter): forward and both gradients equal dot + unmerge."""
+    import torch
+    import cpu_shim
+    from yastn_b200 import backend_b200 as bk
+    cpu_shim.install()
+    try:
+        st = bench_structs()["U1_D64_P1"]["f2m"]
+        md, um = st["dot"]["meta_dot"], st["unmerge"]["meta"]
+        na = max(r[2][1] for r in md); nb = max(r[4][1] for r in md)
+        g = torch.Generator().manual_seed(5)
+        A = torch.rand(na, dtype=torch.float64, generator=g); B = torch.rand(nb, dtype=torch.float64, generator=g)
+        A1, B1 = A.clone().requires_grad_(True), B.clone().requires_grad_(True)
+        A2, B2 = A.clone().requires_grad_(True), B.clone().requires_grad_(True)
+        one = bk.dot_unmerge(A1, B1, md, st["dot"]["Dsize"], um)
+        two = bk.unmerge(bk.dot(A2, B2, md, st["dot"]["Dsize"]), um)
+        assert torch.equal(one, two)
+        G = torch.randn(two.shape, dtype=torch.float64, generator=g)
+        one.backward(G); two.backward(G)
+        assert torch.equal(A1.grad, A2.grad) and torch.equal(B1.grad, B2.grad)
+        out = torch.empty(st["dot"]["Dsize"], dtype=torch.float64)
+        assert bk.dot_unmerge(A, B, md, st["dot"]["Dsize"], um, out=out) is out and torch.equal(out, two.detach())
+    finally:
+        cpu_shim.uninstall()

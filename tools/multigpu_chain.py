@@ -161,6 +161,24 @@ def main():
         lines.append(line)
         if rank == 0:
             print(json.dumps(line), flush=True)
+    # bandwidth of the block exchange when EVERY block changes owner (the recorded chain moves few blocks at 2 ranks: the LPT
+    # owners of both contractions alternate with the charge and the charges of l and r differ by even numbers), and the cost
+    # of a GEMM epilogue that scatters every result block into the neighbour's HBM instead of the local one
+    nxt = [(p + 1) % world for p in produced_by]
+    swap = sharding.PeerExchange(arena, C, slices, produced_by, nxt)
+    contract(sh1, A, F, out=C)
+    swap_ms = timed(lambda: swap.run(C, publish=False), args.iters)
+    nccl_ms = timed(lambda: sharding.redistribute_blocks(C, slices, produced_by, nxt), max(args.iters // 4, 2))
+    local_ms = timed(lambda: contract(sh1, A, F, out=C), args.iters)
+    all_remote = sharding.unmerge_dst_shift(sh1, slices, nxt, rank, shifts)
+    remote_ms = timed(lambda: contract(sh1, A, F, out=C, dst_shift=all_remote), args.iters)
+    line = {"tool": "multigpu_chain", "case": args.case, "dtype": args.dtype, "n_gpus": world, "variant": "swap_all_blocks",
+            "moved_bytes_rank0": swap.elements * isz, "peer_exchange_ms": swap_ms, "peer_exchange_GBps_rank0": swap.elements * isz / swap_ms * 1e-6,
+            "nccl_sendrecv_ms": nccl_ms, "nccl_GBps_rank0": swap.elements * isz / nccl_ms * 1e-6,
+            "contraction1_local_epilogue_ms": local_ms, "contraction1_remote_epilogue_ms": remote_ms}
+    lines.append(line)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     if rank == 0 and args.out:
         with open(args.out, "a") as f:
             for line in lines:

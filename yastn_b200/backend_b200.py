@@ -255,27 +255,31 @@ class _Dot(torch.autograd.Function):
         return gA, gB, None, None
 
 
+def _dot_unmerge_forward(Adata, Bdata, meta_dot, Dsize, meta_unmerge, out=None, dst_shift=None):
+    Adata, Bdata, dtype = _promote(Adata, Bdata)
+    dev = Adata.device.index
+    key = ("dotunm", id(meta_dot), id(meta_unmerge), id(dst_shift), dtype, dev)
+
+    def build():
+        problems, segments = plans.dot_tables(meta_dot)
+        scatter = plans.unmerge_scatter_tables(meta_dot, meta_unmerge, dst_shift)
+        return {"fwd": plans.GemmPlan(problems, segments, _DTYPE_CODE[dtype], dev, scatter), "ref": (meta_unmerge, dst_shift)}
+    ent = _CACHE.get(key, meta_dot, build)
+    if out is None:
+        out = torch.empty(Dsize, dtype=dtype, device=Adata.device)
+    elif out.dtype != dtype or out.numel() != Dsize or out.device != Adata.device or not out.is_contiguous():
+        raise ValueError("yastn_b200.dot_unmerge: out must be a contiguous 1-D tensor of the result's dtype, size and device")
+    _run_gemm(ent["fwd"], Adata, Bdata, out)
+    return out
+
+
 class _DotUnmerge(torch.autograd.Function):
     """dot followed by unmerge in ONE launch: the GEMM epilogue scatters straight into the unmerged block layout
     (reference: the two calls at yastn/tensor/_contractions.py:152-155).  Backward = adjoint unmerge + dot backward."""
 
     @staticmethod
-    def forward(Adata, Bdata, meta_dot, Dsize, meta_unmerge, out=None, dst_shift=None):
-        Adata, Bdata, dtype = _promote(Adata, Bdata)
-        dev = Adata.device.index
-        key = ("dotunm", id(meta_dot), id(meta_unmerge), id(dst_shift), dtype, dev)
-
-        def build():
-            problems, segments = plans.dot_tables(meta_dot)
-            scatter = plans.unmerge_scatter_tables(meta_dot, meta_unmerge, dst_shift)
-            return {"fwd": plans.GemmPlan(problems, segments, _DTYPE_CODE[dtype], dev, scatter), "ref": (meta_unmerge, dst_shift)}
-        ent = _CACHE.get(key, meta_dot, build)
-        if out is None:
-            out = torch.empty(Dsize, dtype=dtype, device=Adata.device)
-        elif out.dtype != dtype or out.numel() != Dsize or out.device != Adata.device or not out.is_contiguous():
-            raise ValueError("yastn_b200.dot_unmerge: out must be a contiguous 1-D tensor of the result's dtype, size and device")
-        _run_gemm(ent["fwd"], Adata, Bdata, out)
-        return out
+    def forward(Adata, Bdata, meta_dot, Dsize, meta_unmerge):
+        return _dot_unmerge_forward(Adata, Bdata, meta_dot, Dsize, meta_unmerge)
 
     @staticmethod
     def setup_context(ctx, inputs, output):
@@ -437,7 +441,7 @@ def dot_unmerge(Adata, Bdata, meta_dot, Dsize, meta_unmerge, out=None, dst_shift
         if out is not None or dst_shift is not None:
             raise ValueError("yastn_b200.dot_unmerge: out= / dst_shift= are forward-only")
         return _DotUnmerge.apply(Adata, Bdata, meta_dot, Dsize, meta_unmerge)
-    return _DotUnmerge.forward(Adata, Bdata, meta_dot, Dsize, meta_unmerge, out, dst_shift)
+    return _dot_unmerge_forward(Adata, Bdata, meta_dot, Dsize, meta_unmerge, out, dst_shift)
 
 
 def transpose_dot_sum(Adata, Bdata, meta_dot, Areshape, Breshape, Aorder, Border, Dsize):

@@ -4,11 +4,13 @@
 // yastn/backend/_backend_torch_backwards.py:315-319, 340-364, 397-408).  The reference issues one
 // strided-copy launch per block; here the host normalises every block move into a "record"
 // (dims sorted by destination stride, unit dims dropped, mergeable dims coalesced) and the device
-// walks a work-item table:
-//   * flat items   — a slice of one large record, destination-linear, fully coalesced writes; reads are
-//                    coalesced too whenever the record keeps its innermost source dim innermost;
-//   * pack items   — many tiny records, one warp per record (tiny blocks dominate block counts);
-//   * tiled items  — (src-fast dim != dst-fast dim) a 2-d slab staged through shared memory so that both
+// walks a work-item table, ONE WARP PER ITEM (about 4096 elements), warps never synchronising with each other:
+//   * flat items   — a slice of one record, destination-linear, coalesced writes, full index decomposition per element;
+//   * row items    — records whose innermost dim is a run contiguous on both sides: long runs move with 16-byte loads,
+//                    short runs (>= 16) resolve the outer indices once per row and share them through warp shuffles
+//                    (the per-element decomposition made the flat path integer-bound for float64);
+//   * pack items   — many small records, one after the other, the next record prefetched while the current one moves;
+//   * tiled items  — (src-fast dim != dst-fast dim) a 2-d slab staged through the warp's shared-memory tile so that both
 //                    the global reads and the global writes are coalesced.
 // HBM-bound: algorithmic bytes = itemsize * (elements read + elements written).
 #include <algorithm>
@@ -20,13 +22,19 @@ namespace yb {
 
 constexpr int kMaxDims = 8;
 constexpr int kCopyThreads = 256;
-constexpr uint32_t kItemElems = 8192;      // elements per flat work item
-constexpr uint32_t kPackElems = 4096;      // target elements per pack of small records
-constexpr int kPackMaxRecs = 256;
-constexpr int kTileDim = 32;               // tiled path: slab is kTileDim x kTileDim elements
-constexpr int kRunUnroll = 4;              // row path: 16-byte loads in flight per lane
-constexpr uint32_t kRowChunk = 32 * kRunUnroll * 2;   // row path: float64 elements a warp moves per trip
-constexpr uint32_t kRowMin = 2048;         // row path only for long contiguous runs (short rows leave lanes idle: measured slower)
+constexpr int kCopyWarps = kCopyThreads / 32;
+constexpr uint32_t kItemElems = 4096;      // largest work item (one warp); plans with little work use smaller items (item_size)
+constexpr uint32_t kSmallRec = 512;        // records below this many elements are packed
+constexpr int kPackMaxRecs = 64;
+constexpr int kTileB = 16;                 // tiled path: slab extent along the source-fast dim
+constexpr int kRunUnroll = 4;              // long-row path: 16-byte loads in flight per lane
+constexpr uint32_t kRowMin = 2048;         // long-row path (16-byte loads) from this run length on
+constexpr uint32_t kRowShortMin = 16;      // short-row path: a 256-element trip then spans at most 17 rows (one lane each)
+
+template <typename T>
+struct TileShape {                          // slab of the tiled path: kTileA (destination-fast) x kTileB (source-fast) elements
+    static constexpr int kTileA = sizeof(T) == 8 ? 32 : 16;
+};
 
 struct alignas(16) CopyRec {
     int64_t src_base, dst_base;
@@ -40,11 +48,13 @@ struct alignas(16) CopyRec {
     uint32_t outer_total;            // product of the other extents
     uint32_t pad_[3];
 };
+static_assert(sizeof(CopyRec) % 16 == 0 && sizeof(CopyRec) / 4 <= 64, "CopyRec is staged by one warp with two words per lane");
+constexpr int kRecWords = sizeof(CopyRec) / 4;
 
 struct CopyItem {
     int32_t rec_begin, rec_end;  // [rec_begin, rec_end) ; a single record unless this is a pack
-    uint32_t e0, ne;             // flat: element range; tiled: slab range
-    int32_t kind;                // 0 flat, 1 pack, 2 tiled, 3 rows (flat range, innermost dim contiguous on both sides)
+    uint32_t e0, ne;             // flat / rows: element range; tiled: slab range
+    int32_t kind;                // 0 flat, 1 pack, 2 tiled, 3 long rows, 4 short rows (3, 4: innermost dim contiguous on both sides)
     int32_t pad_[3];
 };
 
@@ -63,6 +73,15 @@ template <typename T, bool CONJ>
 __device__ __forceinline__ T load_elem(const T* p) {
     T v = *p;
     if constexpr (CONJ) v.y = -v.y;
+    return v;
+}
+
+// Guarded load: the value is defined on both branches (an array filled by predicated loads only is otherwise kept in
+// local memory by the compiler — seen in the SASS as one STL + LDL per element).
+template <typename T, bool CONJ>
+__device__ __forceinline__ T load_if(bool ok, const T* p) {
+    T v = T{};
+    if (ok) v = load_elem<T, CONJ>(p);
     return v;
 }
 
@@ -85,6 +104,27 @@ __device__ __forceinline__ void offsets_of(const REC& rec, uint32_t e, uint32_t&
     dof += e * rec.dstr[0];
 }
 
+// Offsets of row `row` of a record whose innermost dim (index nd-1) is the run: dims [0, nd-1) only.
+template <typename REC>
+__device__ __forceinline__ void row_offsets_of(const REC& rec, uint32_t row, uint32_t& so, uint32_t& dof) {
+    so = 0;
+    dof = 0;
+    const int last = rec.nd - 1;
+#pragma unroll 1
+    for (int k = last - 1; k >= 1; --k) {
+        const uint32_t ext = rec.ext[k];
+        uint32_t q = fdiv(row, ext, rec.mul[k], rec.shr[k]);
+        uint32_t i = row - q * ext;
+        so += i * rec.sstr[k];
+        dof += i * rec.dstr[k];
+        row = q;
+    }
+    if (last >= 1) {
+        so += row * rec.sstr[0];
+        dof += row * rec.dstr[0];
+    }
+}
+
 // Warp-cooperative copy of n contiguous elements.  float64: the source is aligned to 16 bytes by peeling one element,
 // the body moves as double2 loads (stores are double2 too when the destination has the same parity, two scalar stores
 // otherwise); every lane keeps kRunUnroll 16-byte loads in flight.
@@ -102,8 +142,7 @@ __device__ __forceinline__ void copy_run(const T* __restrict__ s, T* __restrict_
         for (uint32_t p0 = lane; p0 < npair; p0 += 32 * kRunUnroll) {
             double2 v[kRunUnroll];
 #pragma unroll
-            for (int u = 0; u < kRunUnroll; ++u)
-                if (p0 + u * 32 < npair) v[u] = s2[p0 + u * 32];
+            for (int u = 0; u < kRunUnroll; ++u) v[u] = load_if<double2, false>(p0 + u * 32 < npair, s2 + p0 + u * 32);
             if (dvec) {
 #pragma unroll
                 for (int u = 0; u < kRunUnroll; ++u)
@@ -122,8 +161,7 @@ __device__ __forceinline__ void copy_run(const T* __restrict__ s, T* __restrict_
         for (uint32_t p0 = lane; p0 < n; p0 += 32 * kRunUnroll) {
             T v[kRunUnroll];
 #pragma unroll
-            for (int u = 0; u < kRunUnroll; ++u)
-                if (p0 + u * 32 < n) v[u] = load_elem<T, CONJ>(s + p0 + u * 32);
+            for (int u = 0; u < kRunUnroll; ++u) v[u] = load_if<T, CONJ>(p0 + u * 32 < n, s + p0 + u * 32);
 #pragma unroll
             for (int u = 0; u < kRunUnroll; ++u)
                 if (p0 + u * 32 < n) d[p0 + u * 32] = v[u];
@@ -131,132 +169,217 @@ __device__ __forceinline__ void copy_run(const T* __restrict__ s, T* __restrict_
     }
 }
 
+// Flat copy of the destination-linear range [e0, end) of one record: every lane keeps 64 bytes of independent loads
+// outstanding before its first store (HBM latency x bandwidth asks for ~35 KB in flight per SM).
+template <typename T, bool CONJ, typename REC>
+__device__ __forceinline__ void copy_flat(const REC& rec, const T* __restrict__ s, T* __restrict__ d, uint32_t e0, uint32_t end, int lane) {
+    constexpr int kUnroll = 64 / sizeof(T);
+    const int nd = rec.nd;
+    for (uint32_t e = e0 + lane; e < end; e += kUnroll * 32) {
+        // index decomposition of kUnroll elements at once, dim by dim: the divisor of a dim is fetched once per trip
+        // (keeping all 8 dims x 5 fields live across the unrolled element loop costs 40 registers and spills)
+        uint32_t rem[kUnroll], so[kUnroll], dof[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            rem[u] = e + u * 32;
+            so[u] = 0;
+            dof[u] = 0;
+        }
+#pragma unroll 1
+        for (int k = nd - 1; k >= 1; --k) {
+            const uint32_t ext = rec.ext[k], mul = rec.mul[k], shr = rec.shr[k], ss = rec.sstr[k], ds = rec.dstr[k];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const uint32_t q = fdiv(rem[u], ext, mul, shr);
+                const uint32_t i = rem[u] - q * ext;
+                so[u] += i * ss;
+                dof[u] += i * ds;
+                rem[u] = q;
+            }
+        }
+        const uint32_t ss0 = rec.sstr[0], ds0 = rec.dstr[0];
+        T v[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            so[u] += rem[u] * ss0;
+            dof[u] += rem[u] * ds0;
+            v[u] = load_if<T, CONJ>(e + u * 32 < end, s + so[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+            if (e + u * 32 < end) d[dof[u]] = v[u];
+    }
+}
+
+// ---- the item kinds; each is its own (non-inlined) function so that the register allocation of one path does not
+// ---- spill the others: inlined into one loop body the five paths needed 80 registers plus 0.4 KB of local memory
+
+// short rows: the innermost dim is a run of L >= kRowShortMin elements contiguous on both sides.  A trip moves 256 (128
+// for complex128) consecutive elements, i.e. at most 256 / L + 2 <= 18 rows: lane j resolves the outer indices of row
+// (first + j) once, every element then costs one division by L and two shuffles instead of a full index decomposition.
 template <typename T, bool CONJ>
-__global__ void __launch_bounds__(kCopyThreads, 3)
+__device__ __noinline__ void item_rows_short(const CopyRec& rec, const T* __restrict__ s, T* __restrict__ d, uint32_t e0, uint32_t end, int lane) {
+    constexpr int kUnroll = 64 / sizeof(T);
+    const int last = rec.nd - 1;
+    const uint32_t L = rec.ext[last], lmul = rec.mul[last], lshr = rec.shr[last];
+    for (uint32_t base = e0; base < end; base += kUnroll * 32) {
+        const uint32_t row0 = __umulhi(base, lmul) >> lshr;
+        uint32_t so_r, dof_r;
+        row_offsets_of(rec, row0 + lane, so_r, dof_r);     // lanes beyond the rows of the trip compute unused values
+        T v[kUnroll];
+        uint32_t dofs[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const uint32_t ee = base + lane + u * 32;
+            const uint32_t row = __umulhi(ee, lmul) >> lshr;
+            const uint32_t col = ee - row * L;
+            const int j = (int)(row - row0) & 31;
+            const uint32_t so = __shfl_sync(0xffffffffu, so_r, j) + col;
+            dofs[u] = __shfl_sync(0xffffffffu, dof_r, j) + col;
+            v[u] = load_if<T, CONJ>(ee < end, s + so);
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+            if (base + lane + u * 32 < end) d[dofs[u]] = v[u];
+    }
+}
+
+// long rows: the warp resolves the outer indices once per row and moves the run with 16-byte loads (copy_run)
+template <typename T, bool CONJ>
+__device__ __noinline__ void item_rows_long(const CopyRec& rec, const T* __restrict__ s, T* __restrict__ d, uint32_t e0, uint32_t end, int lane) {
+    const int last = rec.nd - 1;
+    const uint32_t L = rec.ext[last];
+    uint32_t e = e0;
+    while (e < end) {
+        const uint32_t row = fdiv(e, L, rec.mul[last], rec.shr[last]);
+        const uint32_t col = e - row * L;
+        const uint32_t run = min(L - col, end - e);
+        uint32_t so, dof;
+        row_offsets_of(rec, row, so, dof);
+        copy_run<T, CONJ>(s + so + col, d + dof + col, run, lane);
+        e += run;
+    }
+}
+
+// tiled transpose: slab index -> (outer index, slab coordinates along a and b); the slab goes through the warp's
+// shared-memory tile so that global reads run along b (source-fast) and global writes along a (destination-fast)
+template <typename T, bool CONJ>
+__device__ __noinline__ void item_tiled(const CopyRec& rec, const T* __restrict__ s, T* __restrict__ d, uint32_t slab0, uint32_t slab1,
+                                        T (*tile)[kTileB + 1], int lane) {
+    constexpr int kTileA = TileShape<T>::kTileA;
+    const int da = rec.tile_a, db = rec.tile_b;
+    const uint32_t ea = rec.ext[da], eb = rec.ext[db];
+    const uint32_t sa_s = rec.sstr[da], sa_d = rec.dstr[da];
+    const uint32_t sb_s = rec.sstr[db], sb_d = rec.dstr[db];
+    const uint32_t tiles_a = rec.tiles_a, tiles_b = rec.tiles_b;
+    constexpr int kRowsPerLoad = 32 / kTileB;            // rows of the slab one load instruction covers (2)
+    constexpr int kColsPerStore = 32 / kTileA;           // columns of the slab one store instruction covers (1 or 2)
+    const int rb = lane % kTileB, ra = lane / kTileB;    // read: lane -> (row offset ra, column rb)
+    const int wa = lane % kTileA, wb = lane / kTileA;    // write: lane -> (row wa, column offset wb)
+    for (uint32_t slab = slab0; slab < slab1; ++slab) {
+        uint32_t ta = slab % tiles_a;
+        uint32_t rest = slab / tiles_a;
+        uint32_t tb = rest % tiles_b;
+        uint32_t outer = rest / tiles_b;
+        uint32_t so = 0, dof = 0;
+#pragma unroll 1
+        for (int k = rec.nd - 1; k >= 0; --k) {
+            if (k != da && k != db) {
+                const uint32_t ext = rec.ext[k];
+                uint32_t q = fdiv(outer, ext, rec.mul[k], rec.shr[k]);
+                uint32_t i = outer - q * ext;
+                so += i * rec.sstr[k];
+                dof += i * rec.dstr[k];
+                outer = q;
+            }
+        }
+        const uint32_t a0 = ta * kTileA, b0 = tb * kTileB;
+        T v[kTileA / kRowsPerLoad];
+#pragma unroll
+        for (int j = 0; j < kTileA / kRowsPerLoad; ++j) {
+            const uint32_t ia = a0 + j * kRowsPerLoad + ra, ib = b0 + rb;
+            v[j] = load_if<T, CONJ>(ia < ea && ib < eb, s + so + ia * sa_s + ib * sb_s);
+        }
+#pragma unroll
+        for (int j = 0; j < kTileA / kRowsPerLoad; ++j) tile[j * kRowsPerLoad + ra][rb] = v[j];
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < kTileB / kColsPerStore; ++j) {
+            const uint32_t ib = b0 + j * kColsPerStore + wb, ia = a0 + wa;
+            if (ia < ea && ib < eb) d[dof + ia * sa_d + ib * sb_d] = tile[wa][j * kColsPerStore + wb];
+        }
+        __syncwarp();
+    }
+}
+
+template <typename T, bool CONJ>
+__device__ __noinline__ void item_flat(const CopyRec& rec, const T* __restrict__ s, T* __restrict__ d, uint32_t e0, uint32_t end, int lane) {
+    copy_flat<T, CONJ>(rec, s, d, e0, end, lane);
+}
+
+// pack of small records, one after the other; the next record is fetched while the current one moves
+template <typename T, bool CONJ>
+__device__ __noinline__ void item_pack(const CopyRec* __restrict__ recs, int rec_begin, int rec_end, CopyRec& srec,
+                                       const T* __restrict__ src, T* __restrict__ dst, int lane) {
+    uint32_t w0, w1 = 0;
+    {
+        const uint32_t* g = reinterpret_cast<const uint32_t*>(recs + rec_begin);
+        w0 = g[lane];
+        if (lane + 32 < kRecWords) w1 = g[lane + 32];
+    }
+    for (int r = rec_begin; r < rec_end; ++r) {
+        __syncwarp();
+        uint32_t* sm = reinterpret_cast<uint32_t*>(&srec);
+        sm[lane] = w0;
+        if (lane + 32 < kRecWords) sm[lane + 32] = w1;
+        __syncwarp();
+        if (r + 1 < rec_end) {
+            const uint32_t* g = reinterpret_cast<const uint32_t*>(recs + r + 1);
+            w0 = g[lane];
+            if (lane + 32 < kRecWords) w1 = g[lane + 32];
+        }
+        copy_flat<T, CONJ>(srec, src + srec.src_base, dst + srec.dst_base, 0u, srec.total, lane);
+    }
+}
+
+// One warp = one work item at a time; warps never synchronise with each other, so an SM keeps 32 independent
+// item -> record -> loads -> stores chains in flight (a CTA-wide item pipeline kept 3 and starved on tensors made of
+// thousands of small blocks).
+template <typename T, bool CONJ>
+__global__ void __launch_bounds__(kCopyThreads, 4)
 copy_kernel(const CopyRec* __restrict__ recs, const CopyItem* __restrict__ items, int nitems,
             const T* __restrict__ src, T* __restrict__ dst) {
-    __shared__ CopyRec srec;
-    __shared__ T tile[kTileDim][kTileDim + 1];
-    const int tid = threadIdx.x;
-    for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
+    constexpr int kTileA = TileShape<T>::kTileA;
+    __shared__ CopyRec srecs[kCopyWarps];
+    __shared__ T tiles[kCopyWarps][kTileA][kTileB + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    CopyRec& srec = srecs[warp];
+    const int nwarps = gridDim.x * kCopyWarps;
+    for (int it = blockIdx.x * kCopyWarps + warp; it < nitems; it += nwarps) {
         const CopyItem item = items[it];
         if (item.kind == 1) {
-            // pack of tiny records: one warp per record
-            const int warp = tid >> 5, lane = tid & 31;
-            for (int r = item.rec_begin + warp; r < item.rec_end; r += kCopyThreads / 32) {
-                const CopyRec& rec = recs[r];
-                const T* s = src + rec.src_base;
-                T* d = dst + rec.dst_base;
-                const uint32_t total = rec.total;
-                for (uint32_t e = lane; e < total; e += 32) {
-                    uint32_t so, dof;
-                    offsets_of(rec, e, so, dof);
-                    d[dof] = load_elem<T, CONJ>(s + so);
-                }
-            }
+            item_pack<T, CONJ>(recs, item.rec_begin, item.rec_end, srec, src, dst, lane);
             continue;
         }
-        __syncthreads();  // previous item done with srec / tile
+        __syncwarp();   // the previous item is done with srec / tile
         {
             const uint32_t* g = reinterpret_cast<const uint32_t*>(recs + item.rec_begin);
             uint32_t* sm = reinterpret_cast<uint32_t*>(&srec);
-            for (int w = tid; w < (int)(sizeof(CopyRec) / 4); w += kCopyThreads) sm[w] = g[w];
+            sm[lane] = g[lane];
+            if (lane + 32 < kRecWords) sm[lane + 32] = g[lane + 32];
         }
-        __syncthreads();
+        __syncwarp();
         const T* s = src + srec.src_base;
         T* d = dst + srec.dst_base;
-        if (item.kind == 0) {
-            // HBM latency x bandwidth needs ~35 KB in flight per SM: every thread keeps kUnroll independent loads
-            // outstanding before the first store (one element per thread and trip reaches only half of the bandwidth)
-            constexpr int kUnroll = 64 / sizeof(T);
-            const uint32_t end = item.e0 + item.ne;
-            for (uint32_t e = item.e0 + tid; e < end; e += kUnroll * kCopyThreads) {
-                T v[kUnroll];
-                uint32_t dofs[kUnroll];
-#pragma unroll
-                for (int u = 0; u < kUnroll; ++u) {
-                    const uint32_t ee = e + u * kCopyThreads;
-                    if (ee < end) {
-                        uint32_t so;
-                        offsets_of(srec, ee, so, dofs[u]);
-                        v[u] = load_elem<T, CONJ>(s + so);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < kUnroll; ++u)
-                    if (e + u * kCopyThreads < end) d[dofs[u]] = v[u];
-            }
-        } else if (sizeof(T) == 8 && item.kind == 3) {
-            // rows (float64 only; complex128 elements are 16 bytes already and its flat path runs at 92 % of the HBM peak): the innermost dim is a long run contiguous on both sides.  A warp owns a chunk of the destination-linear
-            // range, resolves the outer indices once per row and moves the run with 16-byte loads (copy_run).
-            const int warp = tid >> 5, lane = tid & 31;
-            const int last = srec.nd - 1;
-            const uint32_t L = srec.ext[last];
-            const uint32_t end = item.e0 + item.ne;
-            for (uint32_t cb = item.e0 + warp * kRowChunk; cb < end; cb += (kCopyThreads / 32) * kRowChunk) {
-                const uint32_t ce = min(cb + kRowChunk, end);
-                uint32_t e = cb;
-                while (e < ce) {
-                    uint32_t row = fdiv(e, L, srec.mul[last], srec.shr[last]);
-                    const uint32_t col = e - row * L;
-                    const uint32_t run = min(L - col, ce - e);
-                    uint32_t so = col, dof = col;
-                    for (int k = last - 1; k >= 1; --k) {
-                        uint32_t q = fdiv(row, srec.ext[k], srec.mul[k], srec.shr[k]);
-                        uint32_t i = row - q * srec.ext[k];
-                        so += i * srec.sstr[k];
-                        dof += i * srec.dstr[k];
-                        row = q;
-                    }
-                    if (last >= 1) {
-                        so += row * srec.sstr[0];
-                        dof += row * srec.dstr[0];
-                    }
-                    copy_run<T, CONJ>(s + so, d + dof, run, lane);
-                    e += run;
-                }
-            }
-        } else {
-            // tiled transpose: slab index -> (outer index, slab coordinates along a and b)
-            const int da = srec.tile_a, db = srec.tile_b;
-            const uint32_t ea = srec.ext[da], eb = srec.ext[db];
-            const uint32_t sa_s = srec.sstr[da], sa_d = srec.dstr[da];
-            const uint32_t sb_s = srec.sstr[db], sb_d = srec.dstr[db];
-            const int tx = tid & 31, ty = tid >> 5;  // 32 x 8
-            for (uint32_t slab = item.e0; slab < item.e0 + item.ne; ++slab) {
-                uint32_t ta = slab % srec.tiles_a;
-                uint32_t rest = slab / srec.tiles_a;
-                uint32_t tb = rest % srec.tiles_b;
-                uint32_t outer = rest / srec.tiles_b;
-                // outer index over the remaining dims (dst order, skipping da/db)
-                uint32_t so = 0, dof = 0;
-#pragma unroll
-                for (int k = kMaxDims - 1; k >= 0; --k) {
-                    if (k < srec.nd && k != da && k != db) {
-                        uint32_t q = fdiv(outer, srec.ext[k], srec.mul[k], srec.shr[k]);
-                        uint32_t i = outer - q * srec.ext[k];
-                        so += i * srec.sstr[k];
-                        dof += i * srec.dstr[k];
-                        outer = q;
-                    }
-                }
-                const uint32_t a0 = ta * kTileDim, b0 = tb * kTileDim;
-                // read: threads contiguous along b (source-fast)
-#pragma unroll
-                for (int j = 0; j < kTileDim; j += 8) {
-                    uint32_t ia = a0 + ty + j, ib = b0 + tx;
-                    if (ia < ea && ib < eb) tile[ty + j][tx] = load_elem<T, CONJ>(s + so + ia * sa_s + ib * sb_s);
-                }
-                __syncthreads();
-                // write: threads contiguous along a (destination-fast)
-#pragma unroll
-                for (int j = 0; j < kTileDim; j += 8) {
-                    uint32_t ib = b0 + ty + j, ia = a0 + tx;
-                    if (ia < ea && ib < eb) d[dof + ia * sa_d + ib * sb_d] = tile[tx][ty + j];
-                }
-                __syncthreads();
-            }
-        }
+        const uint32_t end = item.e0 + item.ne;
+        if (item.kind == 0)
+            item_flat<T, CONJ>(srec, s, d, item.e0, end, lane);
+        else if (item.kind == 4)
+            item_rows_short<T, CONJ>(srec, s, d, item.e0, end, lane);
+        else if (item.kind == 3)
+            item_rows_long<T, CONJ>(srec, s, d, item.e0, end, lane);
+        else
+            item_tiled<T, CONJ>(srec, s, d, item.e0, end, tiles[warp], lane);
     }
 }
 
@@ -365,6 +488,27 @@ void split_to_limits(const HostRec& r, std::vector<HostRec>& out) {
     split_to_limits(hi, out);
 }
 
+int sm_count_of(int device) {
+    static int sm_count[64] = {0};
+    int sms = (device >= 0 && device < 64) ? sm_count[device] : 0;
+    if (sms == 0) {
+        sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        if (device >= 0 && device < 64) sm_count[device] = sms;
+    }
+    return sms;
+}
+
+// Elements per work item.  A warp walks its item trip by trip (256 float64 / 128 complex128 elements per trip, each trip
+// paying the full HBM latency), so a plan needs about two items per resident warp (4 CTAs x 8 warps per SM) before longer
+// items pay off: with fixed 4096-element items a 6 MB merge occupied 25 SMs for 16 dependent trips each.
+uint32_t item_size(int64_t elems, int sms, int itemsize) {
+    const int64_t trip = 32 * (64 / itemsize);
+    const int64_t want = elems / (2ll * sms * 4 * kCopyWarps);
+    const int64_t sz = std::max<int64_t>(trip, std::min<int64_t>(kItemElems, (want + trip - 1) / trip * trip));
+    return (uint32_t)sz;
+}
+
 }  // namespace
 
 extern "C" int yb_copy_plan_create(const int64_t* recs, int64_t nrec, int rank, int itemsize, int device,
@@ -395,6 +539,15 @@ extern "C" int yb_copy_plan_create(const int64_t* recs, int64_t nrec, int rank, 
         split_to_limits(r, host);
     }
 
+    const int tile_a = itemsize == 8 ? TileShape<double>::kTileA : TileShape<double2>::kTileA;
+    const int sms = sm_count_of(device);
+    int64_t all_elems = 0;
+    for (const HostRec& h : host) {
+        int64_t t = 1;
+        for (int k = 0; k < h.nd; ++k) t *= h.ext[k];
+        all_elems += t;
+    }
+    const uint32_t item_elems = item_size(all_elems, sms, itemsize);
     std::vector<CopyRec> drecs;
     std::vector<CopyItem> items;
     int64_t elems = 0, ntiled = 0;
@@ -433,8 +586,8 @@ extern "C" int yb_copy_plan_create(const int64_t* recs, int64_t nrec, int rank, 
         if (c.nd >= 2 && da != db && h.ext[da] >= 8 && h.ext[db] >= 8 && total >= 1024) {
             c.tile_a = da;
             c.tile_b = db;
-            c.tiles_a = (uint32_t)((h.ext[da] + kTileDim - 1) / kTileDim);
-            c.tiles_b = (uint32_t)((h.ext[db] + kTileDim - 1) / kTileDim);
+            c.tiles_a = (uint32_t)((h.ext[da] + tile_a - 1) / tile_a);
+            c.tiles_b = (uint32_t)((h.ext[db] + kTileB - 1) / kTileB);
             c.outer_total = (uint32_t)(total / (h.ext[da] * h.ext[db]));
             ++ntiled;
         }
@@ -444,16 +597,19 @@ extern "C" int yb_copy_plan_create(const int64_t* recs, int64_t nrec, int rank, 
         const CopyRec& c = drecs[i];
         if (c.tile_a >= 0) {
             const uint64_t nslab = (uint64_t)c.tiles_a * c.tiles_b * c.outer_total;
-            const uint32_t per_item = 8;  // 8 slabs of 32x32 = 8192 elements
+            const uint32_t per_item = std::max<uint32_t>(1, item_elems / (uint32_t)(tile_a * kTileB));  // slabs per warp item
             for (uint64_t s0 = 0; s0 < nslab; s0 += per_item) {
                 CopyItem it = {(int32_t)i, (int32_t)i + 1, (uint32_t)s0, (uint32_t)std::min<uint64_t>(per_item, nslab - s0), 2, {0, 0, 0}};
                 items.push_back(it);
             }
-        } else if (c.total >= kPackElems / 4) {
+        } else if (c.total >= kSmallRec) {
             const int last = c.nd - 1;
-            const bool rows = itemsize == 8 && c.sstr[last] == 1 && c.dstr[last] == 1 && c.ext[last] >= kRowMin;
-            for (uint64_t e0 = 0; e0 < c.total; e0 += kItemElems) {
-                CopyItem it = {(int32_t)i, (int32_t)i + 1, (uint32_t)e0, (uint32_t)std::min<uint64_t>(kItemElems, c.total - e0), rows ? 3 : 0, {0, 0, 0}};
+            const bool inner = c.sstr[last] == 1 && c.dstr[last] == 1;   // innermost dim is a run contiguous on both sides
+            int kind = 0;
+            if (inner && itemsize == 8 && c.ext[last] >= kRowMin) kind = 3;
+            else if (inner && c.nd >= 2 && c.ext[last] >= kRowShortMin) kind = 4;
+            for (uint64_t e0 = 0; e0 < c.total; e0 += item_elems) {
+                CopyItem it = {(int32_t)i, (int32_t)i + 1, (uint32_t)e0, (uint32_t)std::min<uint64_t>(item_elems, c.total - e0), kind, {0, 0, 0}};
                 items.push_back(it);
             }
         } else {
@@ -469,7 +625,7 @@ extern "C" int yb_copy_plan_create(const int64_t* recs, int64_t nrec, int rank, 
         for (int j = 0; j < (int)small_idx.size(); ++j) {
             acc += drecs[base + j].total;
             const bool last = (j + 1 == (int)small_idx.size());
-            if (acc >= kPackElems || (base + j + 1 - begin) >= kPackMaxRecs || last) {
+            if (acc >= item_elems || (base + j + 1 - begin) >= kPackMaxRecs || last) {
                 CopyItem it = {begin, base + j + 1, 0, 0, 1, {0, 0, 0}};
                 items.push_back(it);
                 begin = base + j + 1;
@@ -491,16 +647,7 @@ extern "C" int yb_copy_plan_create(const int64_t* recs, int64_t nrec, int rank, 
     if (cudaSetDevice(device) != cudaSuccess) rc = fail(kErrCuda, "yb_copy_plan_create: cudaSetDevice(%d) failed", device);
     if (rc == kOk) rc = plan->recs.upload(drecs.data(), drecs.size() * sizeof(CopyRec));
     if (rc == kOk) rc = plan->items.upload(items.data(), items.size() * sizeof(CopyItem));
-    if (rc == kOk) {
-        static int sm_count[64] = {0};
-        int sms = (device >= 0 && device < 64) ? sm_count[device] : 0;
-        if (sms == 0) {
-            sms = 148;
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-            if (device >= 0 && device < 64) sm_count[device] = sms;
-        }
-        plan->grid = std::max(1, std::min(plan->nitems, sms * 8));
-    }
+    if (rc == kOk) plan->grid = std::max(1, std::min((plan->nitems + kCopyWarps - 1) / kCopyWarps, sms * 4));
     cudaSetDevice(prev);
     if (rc != kOk) {
         plan->recs.release();
