@@ -4,14 +4,14 @@
 // yastn/backend/_backend_torch_backwards.py:315-319, 340-364, 397-408).  The reference issues one
 // strided-copy launch per block; here the host normalises every block move into a "record"
 // (dims sorted by destination stride, unit dims dropped, mergeable dims coalesced) and the device
-// walks a work-item table, ONE WARP PER ITEM (about 4096 elements), warps never synchronising with each other:
+// walks a work-item table, ONE WARP PER ITEM (up to 4096 elements), warps never synchronising with each other:
 //   * flat items   — a slice of one record, destination-linear, coalesced writes, full index decomposition per element;
 //   * row items    — records whose innermost dim is a run contiguous on both sides: long runs move with 16-byte loads,
 //                    short runs (>= 16) resolve the outer indices once per row and share them through warp shuffles
 //                    (the per-element decomposition made the flat path integer-bound for float64);
 //   * pack items   — many small records, one after the other, the next record prefetched while the current one moves;
-//   * tiled items  — (src-fast dim != dst-fast dim) a 2-d slab staged through the warp's shared-memory tile so that both
-//                    the global reads and the global writes are coalesced.
+//   * tiled items  — (src-fast dim != dst-fast dim) a 64-wide 2-d slab staged through shared memory by the whole CTA (second
+//                    phase of the kernel) so that both the global reads and the global writes are 512-byte windows.
 // HBM-bound: algorithmic bytes = itemsize * (elements read + elements written).
 #include <algorithm>
 #include <numeric>
@@ -26,14 +26,18 @@ constexpr int kCopyWarps = kCopyThreads / 32;
 constexpr uint32_t kItemElems = 4096;      // largest work item (one warp); plans with little work use smaller items (item_size)
 constexpr uint32_t kSmallRec = 512;        // records below this many elements are packed
 constexpr int kPackMaxRecs = 64;
-constexpr int kTileB = 16;                 // tiled path: slab extent along the source-fast dim
+constexpr int kTileA = 64;                 // tiled path: slab extent along the destination-fast dim
 constexpr int kRunUnroll = 4;              // long-row path: 16-byte loads in flight per lane
 constexpr uint32_t kRowMin = 2048;         // long-row path (16-byte loads) from this run length on
 constexpr uint32_t kRowShortMin = 16;      // short-row path: a 256-element trip then spans at most 17 rows (one lane each)
 
+// Slab of the tiled (transposing) path: kTileA (destination-fast) x kTileB (source-fast) elements, one CTA per slab.  Both
+// the read windows (kTileB elements) and the write windows (kTileA elements) are 512 bytes or more: block offsets are
+// arbitrary multiples of 8 bytes and DRAM is fetched in 64-byte pieces, so a window of n bytes costs n + 64 on average
+// (ncu on 128-byte windows, the warp-sized 32x16 slab tried first: 1.6x the algorithmic DRAM reads, 3.6 TB/s).
 template <typename T>
-struct TileShape {                          // slab of the tiled path: kTileA (destination-fast) x kTileB (source-fast) elements
-    static constexpr int kTileA = sizeof(T) == 8 ? 32 : 16;
+struct TileShape {
+    static constexpr int kTileB = sizeof(T) == 8 ? 64 : 32;
 };
 
 struct alignas(16) CopyRec {
@@ -261,54 +265,116 @@ __device__ __noinline__ void item_rows_long(const CopyRec& rec, const T* __restr
     }
 }
 
-// tiled transpose: slab index -> (outer index, slab coordinates along a and b); the slab goes through the warp's
-// shared-memory tile so that global reads run along b (source-fast) and global writes along a (destination-fast)
-template <typename T, bool CONJ>
-__device__ __noinline__ void item_tiled(const CopyRec& rec, const T* __restrict__ s, T* __restrict__ d, uint32_t slab0, uint32_t slab1,
-                                        T (*tile)[kTileB + 1], int lane) {
-    constexpr int kTileA = TileShape<T>::kTileA;
+// ---- tiled transpose (its own kernel, one CTA per item): slab index -> (outer index, slab coordinates along a and b); the
+// slab goes through shared memory so that global reads run along b (source-fast) and global writes along a
+// (destination-fast).  Every thread keeps 128 bytes of loads in flight; the four resident CTAs of an SM run out of phase,
+// which overlaps the read and write halves well enough: two explicit pipelines were measured SLOWER on the D=16384
+// float64 transposes (4.56 TB/s as written; 3.87 with the next slab prefetched into registers across the barriers; 3.40
+// with 8/16-byte cp.async into a double-buffered tile at 3 CTAs per SM).
+struct SlabPos {
+    uint32_t so, dof, a0, b0;
+};
+
+template <typename T>
+__device__ __forceinline__ SlabPos slab_position(const CopyRec& rec, uint32_t slab) {
+    constexpr int kTileB = TileShape<T>::kTileB;
     const int da = rec.tile_a, db = rec.tile_b;
-    const uint32_t ea = rec.ext[da], eb = rec.ext[db];
-    const uint32_t sa_s = rec.sstr[da], sa_d = rec.dstr[da];
-    const uint32_t sb_s = rec.sstr[db], sb_d = rec.dstr[db];
-    const uint32_t tiles_a = rec.tiles_a, tiles_b = rec.tiles_b;
-    constexpr int kRowsPerLoad = 32 / kTileB;            // rows of the slab one load instruction covers (2)
-    constexpr int kColsPerStore = 32 / kTileA;           // columns of the slab one store instruction covers (1 or 2)
-    const int rb = lane % kTileB, ra = lane / kTileB;    // read: lane -> (row offset ra, column rb)
-    const int wa = lane % kTileA, wb = lane / kTileA;    // write: lane -> (row wa, column offset wb)
-    for (uint32_t slab = slab0; slab < slab1; ++slab) {
-        uint32_t ta = slab % tiles_a;
-        uint32_t rest = slab / tiles_a;
-        uint32_t tb = rest % tiles_b;
-        uint32_t outer = rest / tiles_b;
-        uint32_t so = 0, dof = 0;
+    uint32_t ta = slab % rec.tiles_a;
+    uint32_t rest = slab / rec.tiles_a;
+    uint32_t tb = rest % rec.tiles_b;
+    uint32_t outer = rest / rec.tiles_b;
+    SlabPos p;
+    p.so = 0;
+    p.dof = 0;
 #pragma unroll 1
-        for (int k = rec.nd - 1; k >= 0; --k) {
-            if (k != da && k != db) {
-                const uint32_t ext = rec.ext[k];
-                uint32_t q = fdiv(outer, ext, rec.mul[k], rec.shr[k]);
-                uint32_t i = outer - q * ext;
-                so += i * rec.sstr[k];
-                dof += i * rec.dstr[k];
-                outer = q;
-            }
+    for (int k = rec.nd - 1; k >= 0; --k) {
+        if (k != da && k != db) {
+            const uint32_t ext = rec.ext[k];
+            uint32_t q = fdiv(outer, ext, rec.mul[k], rec.shr[k]);
+            uint32_t i = outer - q * ext;
+            p.so += i * rec.sstr[k];
+            p.dof += i * rec.dstr[k];
+            outer = q;
         }
-        const uint32_t a0 = ta * kTileA, b0 = tb * kTileB;
-        T v[kTileA / kRowsPerLoad];
+    }
+    p.a0 = ta * kTileA;
+    p.b0 = tb * kTileB;
+    return p;
+}
+
+template <typename T>
+struct SlabRegs {
+    T v[kTileA / kCopyWarps][TileShape<T>::kTileB / 32];
+};
+
+template <typename T, bool CONJ>
+__device__ __forceinline__ void slab_load(const CopyRec& rec, const SlabPos& p, const T* __restrict__ s, SlabRegs<T>& r, int tid) {
+    constexpr int kTileB = TileShape<T>::kTileB;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int da = rec.tile_a, db = rec.tile_b;
+    const uint32_t ea = rec.ext[da], eb = rec.ext[db], sa_s = rec.sstr[da], sb_s = rec.sstr[db];
 #pragma unroll
-        for (int j = 0; j < kTileA / kRowsPerLoad; ++j) {
-            const uint32_t ia = a0 + j * kRowsPerLoad + ra, ib = b0 + rb;
-            v[j] = load_if<T, CONJ>(ia < ea && ib < eb, s + so + ia * sa_s + ib * sb_s);
+    for (int j = 0; j < kTileA / kCopyWarps; ++j) {
+        const uint32_t ia = p.a0 + j * kCopyWarps + warp;
+#pragma unroll
+        for (int h = 0; h < kTileB / 32; ++h) {
+            const uint32_t ib = p.b0 + h * 32 + lane;
+            r.v[j][h] = load_if<T, CONJ>(ia < ea && ib < eb, s + p.so + ia * sa_s + ib * sb_s);
         }
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void slab_to_tile(const SlabRegs<T>& r, T (*tile)[TileShape<T>::kTileB + 1], int tid) {
+    constexpr int kTileB = TileShape<T>::kTileB;
+    const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
-        for (int j = 0; j < kTileA / kRowsPerLoad; ++j) tile[j * kRowsPerLoad + ra][rb] = v[j];
-        __syncwarp();
+    for (int j = 0; j < kTileA / kCopyWarps; ++j)
 #pragma unroll
-        for (int j = 0; j < kTileB / kColsPerStore; ++j) {
-            const uint32_t ib = b0 + j * kColsPerStore + wb, ia = a0 + wa;
-            if (ia < ea && ib < eb) d[dof + ia * sa_d + ib * sb_d] = tile[wa][j * kColsPerStore + wb];
+        for (int h = 0; h < kTileB / 32; ++h) tile[j * kCopyWarps + warp][h * 32 + lane] = r.v[j][h];
+}
+
+template <typename T>
+__device__ __forceinline__ void slab_store(const CopyRec& rec, const SlabPos& p, T* __restrict__ d, T (*tile)[TileShape<T>::kTileB + 1], int tid) {
+    constexpr int kTileB = TileShape<T>::kTileB;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int da = rec.tile_a, db = rec.tile_b;
+    const uint32_t ea = rec.ext[da], eb = rec.ext[db], sa_d = rec.dstr[da], sb_d = rec.dstr[db];
+#pragma unroll
+    for (int j = 0; j < kTileB / kCopyWarps; ++j) {
+        const uint32_t bc = j * kCopyWarps + warp, ib = p.b0 + bc;
+#pragma unroll
+        for (int h = 0; h < kTileA / 32; ++h) {
+            const uint32_t ac = h * 32 + lane, ia = p.a0 + ac;
+            if (ia < ea && ib < eb) d[p.dof + ia * sa_d + ib * sb_d] = tile[ac][bc];
         }
-        __syncwarp();
+    }
+}
+
+template <typename T, bool CONJ>
+__global__ void __launch_bounds__(kCopyThreads, 4)
+tiled_kernel(const CopyRec* __restrict__ recs, const CopyItem* __restrict__ items, int nitems,
+             const T* __restrict__ src, T* __restrict__ dst) {
+    __shared__ T tile[kTileA][TileShape<T>::kTileB + 1];
+    __shared__ CopyRec crec;
+    const int tid = threadIdx.x;
+    for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
+        const CopyItem item = items[it];
+        __syncthreads();   // the previous item is done with crec and the tile
+        if (tid < kRecWords) reinterpret_cast<uint32_t*>(&crec)[tid] = reinterpret_cast<const uint32_t*>(recs + item.rec_begin)[tid];
+        __syncthreads();
+        const T* s = src + crec.src_base;
+        T* d = dst + crec.dst_base;
+        const uint32_t end = item.e0 + item.ne;
+        for (uint32_t slab = item.e0; slab < end; ++slab) {
+            const SlabPos cur = slab_position<T>(crec, slab);
+            SlabRegs<T> regs;
+            slab_load<T, CONJ>(crec, cur, s, regs, tid);
+            slab_to_tile<T>(regs, tile, tid);
+            __syncthreads();
+            slab_store<T>(crec, cur, d, tile, tid);
+            __syncthreads();
+        }
     }
 }
 
@@ -344,14 +410,12 @@ __device__ __noinline__ void item_pack(const CopyRec* __restrict__ recs, int rec
 
 // One warp = one work item at a time; warps never synchronise with each other, so an SM keeps 32 independent
 // item -> record -> loads -> stores chains in flight (a CTA-wide item pipeline kept 3 and starved on tensors made of
-// thousands of small blocks).
+// thousands of small blocks).  Transposing slabs are a separate launch (tiled_kernel).
 template <typename T, bool CONJ>
 __global__ void __launch_bounds__(kCopyThreads, 4)
 copy_kernel(const CopyRec* __restrict__ recs, const CopyItem* __restrict__ items, int nitems,
             const T* __restrict__ src, T* __restrict__ dst) {
-    constexpr int kTileA = TileShape<T>::kTileA;
     __shared__ CopyRec srecs[kCopyWarps];
-    __shared__ T tiles[kCopyWarps][kTileA][kTileB + 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     CopyRec& srec = srecs[warp];
     const int nwarps = gridDim.x * kCopyWarps;
@@ -361,7 +425,7 @@ copy_kernel(const CopyRec* __restrict__ recs, const CopyItem* __restrict__ items
             item_pack<T, CONJ>(recs, item.rec_begin, item.rec_end, srec, src, dst, lane);
             continue;
         }
-        __syncwarp();   // the previous item is done with srec / tile
+        __syncwarp();   // the previous item is done with srec
         {
             const uint32_t* g = reinterpret_cast<const uint32_t*>(recs + item.rec_begin);
             uint32_t* sm = reinterpret_cast<uint32_t*>(&srec);
@@ -376,10 +440,8 @@ copy_kernel(const CopyRec* __restrict__ recs, const CopyItem* __restrict__ items
             item_flat<T, CONJ>(srec, s, d, item.e0, end, lane);
         else if (item.kind == 4)
             item_rows_short<T, CONJ>(srec, s, d, item.e0, end, lane);
-        else if (item.kind == 3)
-            item_rows_long<T, CONJ>(srec, s, d, item.e0, end, lane);
         else
-            item_tiled<T, CONJ>(srec, s, d, item.e0, end, tiles[warp], lane);
+            item_rows_long<T, CONJ>(srec, s, d, item.e0, end, lane);
     }
 }
 
@@ -389,10 +451,10 @@ using namespace yb;
 
 struct yb_copy_plan {
     int itemsize = 0, device = 0;
-    int nitems = 0;
+    int nitems = 0, nwarp_items = 0;
     int64_t elems = 0, nrecs = 0, ntiled = 0;
     DeviceTable recs, items;
-    int grid = 0;
+    int grid = 0, grid_tiled = 0;
 };
 
 namespace {
@@ -539,7 +601,7 @@ extern "C" int yb_copy_plan_create(const int64_t* recs, int64_t nrec, int rank, 
         split_to_limits(r, host);
     }
 
-    const int tile_a = itemsize == 8 ? TileShape<double>::kTileA : TileShape<double2>::kTileA;
+    const int tile_b = itemsize == 8 ? TileShape<double>::kTileB : TileShape<double2>::kTileB;
     const int sms = sm_count_of(device);
     int64_t all_elems = 0;
     for (const HostRec& h : host) {
@@ -549,8 +611,8 @@ extern "C" int yb_copy_plan_create(const int64_t* recs, int64_t nrec, int rank, 
     }
     const uint32_t item_elems = item_size(all_elems, sms, itemsize);
     std::vector<CopyRec> drecs;
-    std::vector<CopyItem> items;
-    int64_t elems = 0, ntiled = 0;
+    std::vector<CopyItem> items, cta_items;
+    int64_t elems = 0, ntiled = 0, nslabs = 0;
     drecs.reserve(host.size());
     // large records first in table order; tiny ones are packed afterwards
     std::vector<int> small_idx;
@@ -583,24 +645,26 @@ extern "C" int yb_copy_plan_create(const int64_t* recs, int64_t nrec, int rank, 
         int da = c.nd - 1, db = 0;
         for (int k = 1; k < c.nd; ++k)
             if (h.sstr[k] < h.sstr[db]) db = k;
-        if (c.nd >= 2 && da != db && h.ext[da] >= 8 && h.ext[db] >= 8 && total >= 1024) {
+        if (c.nd >= 2 && da != db && h.ext[da] >= 16 && h.ext[db] >= 16 && total >= 4096) {
             c.tile_a = da;
             c.tile_b = db;
-            c.tiles_a = (uint32_t)((h.ext[da] + tile_a - 1) / tile_a);
-            c.tiles_b = (uint32_t)((h.ext[db] + kTileB - 1) / kTileB);
+            c.tiles_a = (uint32_t)((h.ext[da] + kTileA - 1) / kTileA);
+            c.tiles_b = (uint32_t)((h.ext[db] + tile_b - 1) / tile_b);
             c.outer_total = (uint32_t)(total / (h.ext[da] * h.ext[db]));
+            nslabs += (int64_t)c.tiles_a * c.tiles_b * c.outer_total;
             ++ntiled;
         }
         drecs.push_back(c);
     }
+    // slabs per CTA item: about two items per resident CTA before items grow (same reasoning as item_size)
+    const uint32_t per_item = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(4, nslabs / (2ll * sms * 4)));
     for (size_t i = 0; i < drecs.size(); ++i) {
         const CopyRec& c = drecs[i];
         if (c.tile_a >= 0) {
             const uint64_t nslab = (uint64_t)c.tiles_a * c.tiles_b * c.outer_total;
-            const uint32_t per_item = std::max<uint32_t>(1, item_elems / (uint32_t)(tile_a * kTileB));  // slabs per warp item
             for (uint64_t s0 = 0; s0 < nslab; s0 += per_item) {
                 CopyItem it = {(int32_t)i, (int32_t)i + 1, (uint32_t)s0, (uint32_t)std::min<uint64_t>(per_item, nslab - s0), 2, {0, 0, 0}};
-                items.push_back(it);
+                cta_items.push_back(it);
             }
         } else if (c.total >= kSmallRec) {
             const int last = c.nd - 1;
@@ -634,10 +698,14 @@ extern "C" int yb_copy_plan_create(const int64_t* recs, int64_t nrec, int rank, 
         }
     }
 
+    const int nwarp_items = (int)items.size();
+    items.insert(items.end(), cta_items.begin(), cta_items.end());   // phase 2 of the kernel: one CTA per item
+
     yb_copy_plan* plan = new yb_copy_plan();
     plan->itemsize = itemsize;
     plan->device = device;
     plan->nitems = (int)items.size();
+    plan->nwarp_items = nwarp_items;
     plan->elems = elems;
     plan->nrecs = (int64_t)host.size();
     plan->ntiled = ntiled;
@@ -647,7 +715,10 @@ extern "C" int yb_copy_plan_create(const int64_t* recs, int64_t nrec, int rank, 
     if (cudaSetDevice(device) != cudaSuccess) rc = fail(kErrCuda, "yb_copy_plan_create: cudaSetDevice(%d) failed", device);
     if (rc == kOk) rc = plan->recs.upload(drecs.data(), drecs.size() * sizeof(CopyRec));
     if (rc == kOk) rc = plan->items.upload(items.data(), items.size() * sizeof(CopyItem));
-    if (rc == kOk) plan->grid = std::max(1, std::min((plan->nitems + kCopyWarps - 1) / kCopyWarps, sms * 4));
+    if (rc == kOk) {
+        plan->grid = std::min((nwarp_items + kCopyWarps - 1) / kCopyWarps, sms * 4);
+        plan->grid_tiled = std::min((int)cta_items.size(), sms * 4);
+    }
     cudaSetDevice(prev);
     if (rc != kOk) {
         plan->recs.release();
@@ -668,6 +739,19 @@ extern "C" int yb_copy_plan_info(const yb_copy_plan* plan, int64_t info[4]) {
     return kOk;
 }
 
+namespace {
+template <typename T, bool CONJ>
+int launch_copy(const yb_copy_plan* plan, const CopyRec* recs, const CopyItem* items, const CopyItem* titems, int ntiled_items,
+                const T* src, T* dst, cudaStream_t st) {
+    if (plan->nwarp_items > 0)
+        copy_kernel<T, CONJ><<<plan->grid, kCopyThreads, 0, st>>>(recs, items, plan->nwarp_items, src, dst);
+    if (ntiled_items > 0) {
+        tiled_kernel<T, CONJ><<<plan->grid_tiled, kCopyThreads, 0, st>>>(recs, titems, ntiled_items, src, dst);
+    }
+    return kOk;
+}
+}  // namespace
+
 extern "C" int yb_copy_run(const yb_copy_plan* plan, const void* src, void* dst, int64_t dst_elems, int flags, void* stream) {
     if (!plan) return fail(kErrArg, "yb_copy_run: plan is null");
     cudaStream_t st = (cudaStream_t)stream;
@@ -679,14 +763,18 @@ extern "C" int yb_copy_run(const yb_copy_plan* plan, const void* src, void* dst,
     if (!src || !dst) return fail(kErrArg, "yb_copy_run: null data pointer");
     const bool conj = (flags & YB_COPY_CONJ) != 0;
     if (conj && plan->itemsize != 16) return fail(kErrArg, "yb_copy_run: conj needs a complex plan");
+    int rc_launch = kOk;
     const CopyRec* recs = (const CopyRec*)plan->recs.ptr;
     const CopyItem* items = (const CopyItem*)plan->items.ptr;
+    const CopyItem* titems = items + plan->nwarp_items;
+    const int ntiled_items = plan->nitems - plan->nwarp_items;
     if (plan->itemsize == 8)
-        copy_kernel<double, false><<<plan->grid, kCopyThreads, 0, st>>>(recs, items, plan->nitems, (const double*)src, (double*)dst);
+        rc_launch = launch_copy<double, false>(plan, recs, items, titems, ntiled_items, (const double*)src, (double*)dst, st);
     else if (conj)
-        copy_kernel<double2, true><<<plan->grid, kCopyThreads, 0, st>>>(recs, items, plan->nitems, (const double2*)src, (double2*)dst);
+        rc_launch = launch_copy<double2, true>(plan, recs, items, titems, ntiled_items, (const double2*)src, (double2*)dst, st);
     else
-        copy_kernel<double2, false><<<plan->grid, kCopyThreads, 0, st>>>(recs, items, plan->nitems, (const double2*)src, (double2*)dst);
+        rc_launch = launch_copy<double2, false>(plan, recs, items, titems, ntiled_items, (const double2*)src, (double2*)dst, st);
+    if (rc_launch != kOk) return rc_launch;
     YB_CUDA(cudaGetLastError());
     return kOk;
 }
