@@ -16,7 +16,8 @@ e2e    = same metric through the backend API with HOST (pinned) operands: H2D of
          D2H of the result, every step; copies run on their own streams so that the transfers of neighbouring
          contractions overlap the kernels (full-duplex PCIe).
 N > 1  = the charge sectors of every contraction are sharded FLOP-balanced over the ranks (no collective on
-         the data path); value = total FLOPs / max-over-ranks time ("strong" scaling).
+         the data path); value = total FLOPs / max-over-ranks time ("strong" scaling).  In the e2e leg every rank moves
+         only the operand blocks its sectors read and the result blocks it writes; the byte counts are job totals.
 """
 import argparse
 import json
@@ -51,6 +52,25 @@ def load_cases(sizes):
 
 def case_flops(stage, cplx):
     return sum((8 if cplx else 2) * Da[0] * Da[1] * Db[1] for (_, _, _, Da, _, Db) in stage["dot"]["meta_dot"])
+
+
+def _coalesce(slices):
+    out = []
+    for lo, hi in sorted(s for s in slices if s[1] > s[0]):
+        if out and lo <= out[-1][1]:
+            out[-1][1] = max(out[-1][1], hi)
+        else:
+            out.append([lo, hi])
+    return [tuple(x) for x in out]
+
+
+def shard_ranges(stage):
+    """Storage ranges a rank touches for one sharded contraction: (A blocks read, B blocks read, result blocks written)."""
+    md = stage["dot"]["meta_dot"]
+    a = [r[1] for r in stage["merge_a"]["meta_mrg"]] if stage["merge_a"] is not None else [r[2] for r in md]
+    b = [r[1] for r in stage["merge_b"]["meta_mrg"]] if stage["merge_b"] is not None else [r[4] for r in md]
+    c = [r[0] for r in stage["unmerge"]["meta"]] if stage["unmerge"] is not None else [r[0] for r in md]
+    return _coalesce(a), _coalesce(b), _coalesce(c)
 
 
 class ClockSampler:
@@ -180,6 +200,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL logs (its version banner under NCCL_DEBUG=VERSION) go to stdout by default: keep stdout to the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     cplx = args.dtype == "c128"
     tdt = torch.complex128 if cplx else torch.float64
@@ -274,17 +296,32 @@ def main():
     if not args.no_e2e:
         host = [(w["A"].cpu().pin_memory(), w["B"].cpu().pin_memory()) for w in work]
         out_host = [torch.empty(w["stage"]["dot"]["Dsize"], dtype=tdt).pin_memory() for w in work]
-        h2d = sum(a.numel() * a.element_size() + b.numel() * b.element_size() for a, b in host)
-        d2h = sum(o.numel() * o.element_size() for o in out_host)
+        # N > 1: a rank moves only the operand blocks its sectors read and the result blocks it produces (coalesced ranges of
+        # the 1-D storage); N = 1: the whole tensors
+        ranges = [shard_ranges(w["stage"]) if world > 1 else None for w in work]
+        isz_ = 16 if cplx else 8
+        if world > 1:
+            h2d = sum(isz_ * sum(hi - lo for lo, hi in r[0] + r[1]) for r in ranges)
+            d2h = sum(isz_ * sum(hi - lo for lo, hi in r[2]) for r in ranges)
+        else:
+            h2d = sum(a.numel() * a.element_size() + b.numel() * b.element_size() for a, b in host)
+            d2h = sum(o.numel() * o.element_size() for o in out_host)
         e2e_steps = max(1, min(args.steps, 5))
         # three streams: H2D of the next contraction and D2H of the previous one overlap the kernels of the current one
         # (PCIe is full duplex); every contraction still does H2D -> merge/merge/GEMM+unmerge -> D2H inside the timed region
         s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         def e2e_pass():
             cur = torch.cuda.current_stream(dev)
-            for w, (ha, hb), ho in e2e_order:
+            for w, (ha, hb), ho, rg in e2e_order:
                 with torch.cuda.stream(s_in):
-                    A = ha.to(dev, non_blocking=True); B = hb.to(dev, non_blocking=True)
+                    if rg is None:
+                        A = ha.to(dev, non_blocking=True); B = hb.to(dev, non_blocking=True)
+                    else:
+                        A = torch.empty(ha.numel(), dtype=tdt, device=dev); B = torch.empty(hb.numel(), dtype=tdt, device=dev)
+                        for lo, hi in rg[0]:
+                            A[lo:hi].copy_(ha[lo:hi], non_blocking=True)
+                        for lo, hi in rg[1]:
+                            B[lo:hi].copy_(hb[lo:hi], non_blocking=True)
                     ready = torch.cuda.Event(); ready.record(s_in)
                 cur.wait_event(ready)
                 A.record_stream(cur); B.record_stream(cur)
@@ -292,11 +329,15 @@ def main():
                 done = torch.cuda.Event(); done.record(cur)
                 s_out.wait_event(done)
                 with torch.cuda.stream(s_out):
-                    ho.copy_(C, non_blocking=True)
+                    if rg is None:
+                        ho.copy_(C, non_blocking=True)
+                    else:
+                        for lo, hi in rg[2]:
+                            ho[lo:hi].copy_(C[lo:hi], non_blocking=True)
                 C.record_stream(s_out)
         # largest contraction first: its D2H (2 GB at D=16384) then overlaps the H2D and kernels of the others; consecutive
         # steps are not joined (the copy streams are ordered by events only), the timed region ends when the last D2H lands
-        e2e_order = sorted(zip(work, host, out_host), key=lambda t: -t[2].numel())
+        e2e_order = sorted(zip(work, host, out_host, ranges), key=lambda t: -t[2].numel())
         def e2e_join():
             cur = torch.cuda.current_stream(dev)
             cur.wait_stream(s_in)
@@ -318,6 +359,10 @@ def main():
         t = torch.tensor([ms, gemm_ms, float(own_flops), e2e_ms if not args.no_e2e else 0.0], dtype=torch.float64, device=dev)
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         ms, e2e_max = float(tmax[0]), float(tmax[3])
+        if not args.no_e2e:       # bytes moved by the whole job
+            tb = torch.tensor([float(h2d), float(d2h)], dtype=torch.float64, device=dev)
+            dist.all_reduce(tb)
+            h2d, d2h = int(tb[0]), int(tb[1])
     else:
         e2e_max = e2e_ms if not args.no_e2e else 0.0
     if not args.no_e2e:

@@ -114,3 +114,28 @@ def test_assignment_is_deterministic_balanced_and_complete(name):
             for rec in (sh["unmerge"]["meta"] if sh["unmerge"] is not None else sh["dot"]["meta_dot"]):
                 cover[rec[0][0]:rec[0][1]] += 1
         assert (cover == 1).all()
+
+
+@pytest.mark.parametrize("name", ["U1_D1024_P1", "U1_D16384_P2", "U1xU1_D4096_P1"])
+def test_bench_shard_ranges_cover_exactly_what_a_rank_touches(name):
+    """bench.py e2e leg at N > 1: the coalesced storage ranges a rank copies in / out are exactly the operand blocks its
+    sharded metas read and the result blocks they write, and the result ranges of all ranks tile the result."""
+    import bench
+    st = bench_structs()[name]["f2m"]
+    for world in (2, 8):
+        cover = np.zeros(st["dot"]["Dsize"], dtype=np.int8)
+        for r in range(world):
+            sh, _ = sharding.shard_f2m(st, r, world)
+            a, b, c = bench.shard_ranges(sh)
+            for rng, key in ((a, "merge_a"), (b, "merge_b")):
+                assert all(x[1] <= y[0] for x, y in zip(rng, rng[1:]))          # sorted, disjoint
+                need = np.zeros(max(hi for _, hi in rng), dtype=bool)
+                got = np.zeros_like(need)
+                for rec in sh[key]["meta_mrg"]:
+                    need[rec[1][0]:rec[1][1]] = True
+                for lo, hi in rng:
+                    got[lo:hi] = True
+                assert np.array_equal(need, got)
+            for lo, hi in c:
+                cover[lo:hi] += 1
+        assert (cover == 1).all()
