@@ -187,6 +187,12 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # stdout carries exactly one JSON line: everything else that libraries print there (NCCL's version banner is written
+    # to fd 1 whatever NCCL_DEBUG_FILE says) is sent to stderr by swapping the descriptors for the duration of the run
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     from yastn_b200 import backend_b200 as bk
@@ -200,8 +206,6 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL logs (its version banner under NCCL_DEBUG=VERSION) go to stdout by default: keep stdout to the one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     cplx = args.dtype == "c128"
     tdt = torch.complex128 if cplx else torch.float64
@@ -406,7 +410,7 @@ def main():
             line["e2e"] = e2e
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(cplx)
-        print(json.dumps(line))
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
