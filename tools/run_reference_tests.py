@@ -18,7 +18,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 DEFAULT_FILES = ["tensor/test_tensordot.py", "tensor/test_ncon_einsum.py", "tensor/test_fuse_hard.py", "tensor/test_transpose.py",
                  "tensor/test_tensordot_ad.py", "tensor/test_fuse_meta.py", "tensor/test_cache.py", "mps/test_dmrg.py", "mps/test_env.py",
-                 "mps/test_tdvp.py"]
+                 "mps/test_tdvp.py",
+                 # decompositions (activate() also installs the sector-parallel svd / qr / eigh of yastn_b200.decomp)
+                 "tensor/test_svd.py", "tensor/test_qr.py", "tensor/test_eigh.py"]
 
 
 class Tally:
