@@ -358,3 +358,35 @@ def test_device_sector_matching_bit_exact():
     e = np.zeros((0, 1), dtype=np.int64), np.zeros((0, 2), dtype=np.int64), np.zeros(0, dtype=np.int64)
     problems, segments, csize = sectors.match_sectors(*e, *e, device=0)
     assert problems.shape == (0, 6) and csize == 0
+
+
+@pytest.mark.parametrize("name", ["U1_D1024_P1", "U1_D2048_P3", "U1_D4096_T1"])
+def test_cuda_graph_capture_and_replay(bk, name):
+    """The run calls allocate nothing and never synchronise (include/yastn_b200.h): a whole tensordot — merges (copy and tiled
+    kernels, the zero-fill memset), grouped GEMM with stream-K partials (P3 splits tiles over CTAs; their flags must rest at 0
+    between launches) and unmerge — is captured into a CUDA graph once the plans exist and replayed on new operand values."""
+    case = bench_structs()[name]
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    A = torch.rand(case["a"]["size"], dtype=torch.float64, device="cuda", generator=gen)
+    B = torch.rand(case["b"]["size"], dtype=torch.float64, device="cuda", generator=gen)
+    A2, B2 = torch.rand_like(A), torch.rand_like(B)
+    _run_f2m(bk, A, B, case)                       # builds the plans (plan creation uploads tables: not capturable)
+    expect2 = _run_f2m(bk, A2, B2, case).clone()
+    expect1 = _run_f2m(bk, A, B, case).clone()
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        _run_f2m(bk, A, B, case)                   # warm the capture stream's allocator pool
+    torch.cuda.current_stream().wait_stream(side)
+    with torch.cuda.graph(graph):
+        out = _run_f2m(bk, A, B, case)
+    for _ in range(2):
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, expect1)
+    A.copy_(A2); B.copy_(B2)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, expect2)

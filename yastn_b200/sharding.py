@@ -64,7 +64,8 @@ def shard_f2m(stage, rank, world, panels=True):
     ``stage`` = dict(merge_a, merge_b, dot, unmerge) in the reference's meta formats (None = stage skipped).
     Offsets are kept global, so shards write disjoint parts of full-size buffers and the union over ranks is
     the unsharded result.  With ``panels`` sectors may be split into row panels (see ``partition_rows``): the ranks sharing a
-    sector each merge its operands (HBM-bound, cheap) and multiply only their rows; without, whole sectors are dealt by LPT.
+    sector each merge its B operand and the source blocks of A that fill their own rows, and multiply only those rows;
+    without, whole sectors are dealt by LPT.
     Returns (sharded_stage, owned_flops).
     """
     meta_dot = stage["dot"]["meta_dot"]
@@ -82,6 +83,10 @@ def shard_f2m(stage, rank, world, panels=True):
         mine.append((pslc, (r1 - r0, N), (sla[0] + r0 * K, sla[0] + r1 * K), (r1 - r0, K), slb, Db))
         panel_of.setdefault(slc, []).append((r0, r1, pslc))
     out = {"dot": {"meta_dot": tuple(mine), "Dsize": stage["dot"]["Dsize"]}}
+    # rows of every merged A block that this rank multiplies (several panels of one sector may land on one rank)
+    a_rows = {}
+    for (p, r0, r1) in units:
+        a_rows.setdefault(meta_dot[p][2], []).append((r0, r1))
     for key, keep in (("merge_a", a_slices), ("merge_b", b_slices)):
         m = stage[key]
         if m is None:
@@ -89,7 +94,13 @@ def shard_f2m(stage, rank, world, panels=True):
             continue
         new = tuple(x for x in m["meta_new"] if x[2] in keep)
         tns = {x[0] for x in new}
-        out[key] = {"order": m["order"], "meta_new": new, "meta_mrg": tuple(x for x in m["meta_mrg"] if x[0] in tns), "Dsize": m["Dsize"]}
+        recs = tuple(x for x in m["meta_mrg"] if x[0] in tns)
+        if key == "merge_a" and panels:
+            # a source block fills the rows Dslc[0] of its merged block: only blocks that intersect this rank's row panels are
+            # merged (and, in an end-to-end run, copied to the device); the other rows of the merged block are never read
+            rows_of = {x[0]: a_rows[x[2]] for x in new}
+            recs = tuple(x for x in recs if any(x[3][0][0] < r1 and r0 < x[3][0][1] for (r0, r1) in rows_of[x[0]]))
+        out[key] = {"order": m["order"], "meta_new": new, "meta_mrg": recs, "Dsize": m["Dsize"]}
     u = stage["unmerge"]
     if u is None:
         out["unmerge"] = None
