@@ -168,3 +168,27 @@ def test_fused_dot_unmerge_autograd_matches_two_calls_shim():
         assert bk.dot_unmerge(A, B, md, st["dot"]["Dsize"], um, out=out) is out and torch.equal(out, two.detach())
     finally:
         cpu_shim.uninstall()
+
+
+def test_fused_dot_unmerge_falls_back_when_lookup_tables_would_be_huge(monkeypatch):
+    """Tall-and-skinny products (10^6+ rows per merged block) would need row/column lookup tables larger than the operands:
+    above the limit dot_unmerge runs as dot + unmerge, same result, also into a caller-provided ``out``."""
+    import torch
+    import cpu_shim
+    from yastn_b200 import backend_b200 as bk
+    cpu_shim.install()
+    try:
+        st = bench_structs()["U1_D64_P1"]["f2m"]
+        md, um = st["dot"]["meta_dot"], st["unmerge"]["meta"]
+        na = max(r[2][1] for r in md); nb = max(r[4][1] for r in md)
+        g = torch.Generator().manual_seed(6)
+        A = torch.rand(na, dtype=torch.float64, generator=g); B = torch.rand(nb, dtype=torch.float64, generator=g)
+        fused = bk.dot_unmerge(A, B, md, st["dot"]["Dsize"], um)
+        monkeypatch.setattr(bk, "_SCATTER_TABLE_LIMIT", 1)
+        bk.clear_plan_cache()
+        two = bk.dot_unmerge(A, B, md, st["dot"]["Dsize"], um)
+        out = torch.empty_like(two)
+        assert bk.dot_unmerge(A, B, md, st["dot"]["Dsize"], um, out=out) is out
+        assert torch.equal(fused, two) and torch.equal(fused, out)
+    finally:
+        cpu_shim.uninstall()

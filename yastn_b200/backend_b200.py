@@ -255,16 +255,30 @@ class _Dot(torch.autograd.Function):
         return gA, gB, None, None
 
 
+_SCATTER_TABLE_LIMIT = 1 << 19    # rows + columns of all merged blocks whose lookup tables the fused epilogue may hold
+
+
 def _dot_unmerge_forward(Adata, Bdata, meta_dot, Dsize, meta_unmerge, out=None, dst_shift=None):
     Adata, Bdata, dtype = _promote(Adata, Bdata)
     dev = Adata.device.index
     key = ("dotunm", id(meta_dot), id(meta_unmerge), id(dst_shift), dtype, dev)
 
     def build():
+        # the scatter epilogue looks every row and column of a merged block up in a table: for tall-and-skinny products (an
+        # environment update has blocks of 10^6..10^7 rows and a handful of columns) those tables would be larger than the
+        # operands (measured: 48 ms of plan creation per call in a D=4096 DMRG sweep) -> two launches instead
+        if dst_shift is None and sum(rec[1][0] + rec[1][1] for rec in meta_dot) > _SCATTER_TABLE_LIMIT:
+            return {"fwd": None, "ref": (meta_unmerge, dst_shift)}
         problems, segments = plans.dot_tables(meta_dot)
         scatter = plans.unmerge_scatter_tables(meta_dot, meta_unmerge, dst_shift)
         return {"fwd": plans.GemmPlan(problems, segments, _DTYPE_CODE[dtype], dev, scatter), "ref": (meta_unmerge, dst_shift)}
     ent = _CACHE.get(key, meta_dot, build)
+    if ent["fwd"] is None:
+        res = _Unmerge.forward(_Dot.forward(Adata, Bdata, meta_dot, Dsize), meta_unmerge)
+        if out is None:
+            return res
+        out.copy_(res)
+        return out
     if out is None:
         out = torch.empty(Dsize, dtype=dtype, device=Adata.device)
     elif out.dtype != dtype or out.numel() != Dsize or out.device != Adata.device or not out.is_contiguous():
