@@ -54,10 +54,17 @@ def init(self, problems, segments, dtype_code, device, scatter=None):
     orig_init(self, problems, segments, dtype_code, device, scatter)
     self._scat = scatter is not None
     self._shape = (len(problems), None if scatter is None else int(len(scatter[6])))
+    dt = time.perf_counter() - t0
     if scatter is not None:
-        T["create_s"] += time.perf_counter() - t0
+        T["create_s"] += dt
         T["create_n"] += 1
         T["nscat_max"] = max(T["nscat_max"], int(len(scatter[1])) - 1)
+    else:
+        tiles = self.info()["tiles"]
+        kind = "plain_create_many_tiles" if tiles > 50000 else "plain_create"
+        T[kind + "_s"] = T.get(kind + "_s", 0.0) + dt
+        T[kind + "_n"] = T.get(kind + "_n", 0) + 1
+        T["tiles_max"] = max(T.get("tiles_max", 0), tiles)
 
 
 SK = {"skinny_s": 0.0, "skinny_n": 0, "other_s": 0.0, "other_n": 0, "skinny_macs": 0, "other_macs": 0}
