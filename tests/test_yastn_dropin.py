@@ -387,3 +387,24 @@ def test_bs_to_tds_matches_reference_meta(sym):
     for (sl, Dlr, pairs), (sl_r, Dlr_r, pairs_r) in zip(md, meta_dot):
         assert sl == tuple(sl_r) and Dlr == tuple(int(x) for x in Dlr_r)
         assert sorted(pairs) == sorted(tuple(p) for p in pairs_r)
+
+
+@pytest.mark.parametrize("dtype", ["float64", "complex128"])
+def test_vdot_is_one_grouped_gemm(device, dtype):
+    """yastn.vdot on tensors with different block structures (meta path, yastn/tensor/_contractions.py:590-630): all common
+    blocks in one launch, every conj combination, against the numpy backend."""
+    ref, our = cfgs("U1", "fuse_to_matrix", device)
+    ref.backend.random_seed(11)
+    a = yastn.rand(config=ref, s=(-1, 1, 1), t=((-1, 0, 1, 2), (-1, 0, 1), (-2, -1, 0, 1, 2)), D=((2, 3, 4, 5), (3, 2, 4), (1, 5, 6, 2, 3)), dtype=dtype)
+    b = yastn.rand(config=ref, s=(-1, 1, 1), t=((-1, 0, 1), (-1, 0, 1), (-1, 0, 1, 2)), D=((2, 3, 4), (3, 2, 4), (5, 6, 2, 3)), dtype=dtype)
+    A, B = mirror(a, our), mirror(b, our)
+    before = yastn_backend.call_counts()["native"]["vdot"]
+    for conj in ((1, 0), (0, 1), (0, 0), (1, 1)):
+        x, y = (a, b) if conj[0] != conj[1] else (a, b.conj())      # signatures must match after the conjugations
+        X, Y = (A, B) if conj[0] != conj[1] else (A, B.conj())
+        r = yastn.vdot(x, y, conj=conj)
+        c = yastn.vdot(X, Y, conj=conj)
+        assert abs(complex(c) - complex(r)) <= TOL * max(abs(complex(r)), 1.0)
+    assert yastn_backend.call_counts()["native"]["vdot"] >= before + 4
+    # same structure: the reference takes its single-dot path, no meta
+    assert abs(complex(yastn.vdot(A, A)) - complex(yastn.vdot(a, a))) <= TOL * abs(complex(yastn.vdot(a, a)))

@@ -466,6 +466,29 @@ def transpose_dot_sum(Adata, Bdata, meta_dot, Areshape, Breshape, Aorder, Border
     return _tds_forward(Adata, Bdata, meta_dot, Areshape, Breshape, Aorder, Border, Dsize)
 
 
+def vdot(Adata, Bdata, meta):
+    """``sum_ii dot(Adata[sla_ii], Bdata[slb_ii])`` over the common blocks of two tensors (yastn/backend/backend_torch.py:537-546,
+    called by yastn.vdot, yastn/tensor/_contractions.py:590-630, in every Lanczos step): the reference runs one ``torch.dot``
+    per block; here all blocks are 1 x 1 problems of ONE grouped-GEMM launch (the long contraction index is shared out over the
+    CTAs by stream-K) followed by one sum.  Conjugation arrives as torch's lazy conj bit, as for ``dot``.  Forward only."""
+    _check(Adata, "vdot")
+    _check(Bdata, "vdot")
+    Adata, Bdata, dtype = _promote(Adata, Bdata)
+    n = len(meta)
+    if n == 0:
+        return torch.zeros((), dtype=dtype, device=Adata.device)
+    dev = Adata.device.index
+    key = ("vdot", id(meta), dtype, dev)
+
+    def build():
+        problems, segments = plans.vdot_tables(meta)
+        return {"fwd": plans.GemmPlan(problems, segments, _DTYPE_CODE[dtype], dev)}
+    ent = _CACHE.get(key, meta, build)
+    tmp = torch.empty(n, dtype=dtype, device=Adata.device)
+    _run_gemm(ent["fwd"], Adata, Bdata, tmp)
+    return torch.sum(tmp)
+
+
 _BS_CACHE = plans.PlanCache(maxsize=1024)
 
 

@@ -171,6 +171,27 @@ def dot_tables(meta_dot):
     return problems, segments
 
 
+def vdot_tables(meta):
+    """GEMM tables of backend.vdot (yastn/backend/backend_torch.py:537-546): one 1 x 1 problem per pair of common blocks,
+    ``C[ii] = sum_k A[sla + k] * B[slb + k]``; the contraction index is contiguous in both operands."""
+    n = len(meta)
+    problems = np.empty((n, 6), dtype=I64)
+    segments = np.empty((n, 7), dtype=I64)
+    if n == 0:
+        return problems, segments
+    tab = _table(meta, n)                              # [sla(2), slb(2)]
+    if tab.shape[1] != 4:
+        raise ValueError("vdot: unexpected meta layout")
+    K = tab[:, 1] - tab[:, 0]
+    if (K != tab[:, 3] - tab[:, 2]).any():
+        raise ValueError("vdot: blocks of different size")
+    idx = np.arange(n, dtype=I64)
+    problems[:, 0], problems[:, 1], problems[:, 2], problems[:, 3], problems[:, 4], problems[:, 5] = 1, 1, idx, 1, idx, idx + 1
+    segments[:, 0], segments[:, 1], segments[:, 2], segments[:, 3] = K, tab[:, 0], K, 1
+    segments[:, 4], segments[:, 5], segments[:, 6] = tab[:, 2], 1, K
+    return problems, segments
+
+
 def dot_backward_tables(meta_dot):
     """GEMM tables of the adjoints  A_b += C_b @ B^H  and  B_b += A^H @ C_b  (grouped by target block).
 

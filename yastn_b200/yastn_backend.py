@@ -30,7 +30,7 @@ _HOT = _bk.HOT_FUNCTIONS
 _DECOMP = ("svd", "svdvals", "eigh", "qr")
 _NATIVE = (torch.float64, torch.complex128)
 _state = {"module": {}, "saved": None, "saved_f2m": None, "saved_decomp": None,
-          "calls": {name: 0 for name in _HOT + ("dot_unmerge", "kernel_tensordot_bs")}, "delegated": {name: 0 for name in _HOT}}
+          "calls": {name: 0 for name in _HOT + ("dot_unmerge", "kernel_tensordot_bs", "vdot")}, "delegated": {name: 0 for name in _HOT}}
 
 
 def _stock():
@@ -104,8 +104,18 @@ def _make_hot(stock_fns, delegate):
         calls["kernel_tensordot_bs"] += 1
         return _bk.kernel_tensordot_bs(a, b, *args, **kwargs)
 
+    def vdot(Adata, Bdata, meta):
+        """Block loop of torch.dot calls (backend_torch.py:537-546) as one grouped-GEMM launch; inputs that require grad, or are
+        not float64 / complex128 CUDA tensors, keep the reference's differentiable loop."""
+        grad = torch.is_grad_enabled() and (Adata.requires_grad or Bdata.requires_grad)
+        if grad or len(meta) < 2 or not _native(Adata, Bdata):
+            return stock_fns["vdot"](Adata, Bdata, meta)
+        calls["vdot"] += 1
+        return _bk.vdot(Adata, Bdata, meta)
+
     return {"transpose_and_merge": transpose_and_merge, "unmerge": unmerge, "transpose": transpose, "dot": dot,
-            "transpose_dot_sum": transpose_dot_sum, "dot_unmerge": dot_unmerge, "kernel_tensordot_bs": kernel_tensordot_bs}
+            "transpose_dot_sum": transpose_dot_sum, "dot_unmerge": dot_unmerge, "kernel_tensordot_bs": kernel_tensordot_bs,
+            "vdot": vdot}
 
 
 def _make_decomp(stock):
@@ -124,7 +134,7 @@ def module(delegate_other_dtypes=True, bs_boundary=False):
     variant = bool(bs_boundary)
     if variant not in _state["module"]:
         stock = _stock()
-        saved = _state["saved"] or {n: getattr(stock, n) for n in _HOT}
+        saved = _state["saved"] or {n: getattr(stock, n) for n in _HOT + ("vdot",)}
         mod = types.ModuleType("yastn_b200_backend" + ("_bs" if variant else ""),
                                "stock yastn torch backend with the B200 contraction kernels")
         for name in dir(stock):
@@ -145,9 +155,10 @@ def activate(delegate_other_dtypes=True):
     """Install mode B: rebind the five hot functions on ``yastn.backend.backend_torch`` itself."""
     stock = _stock()
     if _state["saved"] is None:
-        _state["saved"] = {n: getattr(stock, n) for n in _HOT}
+        _state["saved"] = {n: getattr(stock, n) for n in _HOT + ("vdot",)}
     for name, fn in _make_hot(_state["saved"], delegate_other_dtypes).items():
-        setattr(stock, name, fn)
+        if name in _state["saved"] or name in ("dot_unmerge", "kernel_tensordot_bs"):
+            setattr(stock, name, fn)
     for name, fn in _make_decomp(stock).items():
         setattr(stock, name, fn)
     return stock
