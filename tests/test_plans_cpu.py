@@ -192,3 +192,26 @@ def test_fused_dot_unmerge_falls_back_when_lookup_tables_would_be_huge(monkeypat
         assert torch.equal(fused, two) and torch.equal(fused, out)
     finally:
         cpu_shim.uninstall()
+
+
+def test_vdot_tables_pass_plan_validation_for_huge_blocks():
+    """A joined vdot slice can hold 10^8 elements: the C ABI must accept the 1 x 1 problems (no stride limit hit).  Without a
+    GPU plan creation stops at cudaSetDevice, i.e. AFTER the table validation — which is what is checked here."""
+    import ctypes
+    meta = (((0, 150_000_000), (7, 150_000_007)), ((150_000_000, 150_000_003), (150_000_007, 150_000_010)))
+    problems, segments = plans.vdot_tables(meta)
+    A = np.arange(12, dtype=np.float64); B = np.arange(20, dtype=np.float64)
+    small = (((0, 5), (3, 8)), ((5, 12), (10, 17)))
+    p2, s2 = plans.vdot_tables(small)
+    out = exec_gemm(p2, s2, A, B, np.zeros(2))
+    assert np.allclose(out, [A[0:5] @ B[3:8], A[5:12] @ B[10:17]])
+    lib = _lib.load()
+    for dtype_code in (_lib.YB_F64, _lib.YB_C128):
+        h = ctypes.c_void_p()
+        rc = lib.yb_gemm_plan_create(problems.ctypes.data_as(ctypes.c_void_p), 2, segments.ctypes.data_as(ctypes.c_void_p), 2,
+                                     dtype_code, 0, ctypes.byref(h))
+        msg = lib.yb_last_error().decode()
+        if rc == 0:
+            lib.yb_gemm_plan_destroy(h)
+        else:
+            assert "cudaSetDevice" in msg or "CUDA" in msg or "cuda" in msg, msg

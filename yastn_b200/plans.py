@@ -187,8 +187,10 @@ def vdot_tables(meta):
         raise ValueError("vdot: blocks of different size")
     idx = np.arange(n, dtype=I64)
     problems[:, 0], problems[:, 1], problems[:, 2], problems[:, 3], problems[:, 4], problems[:, 5] = 1, 1, idx, 1, idx, idx + 1
-    segments[:, 0], segments[:, 1], segments[:, 2], segments[:, 3] = K, tab[:, 0], K, 1
-    segments[:, 4], segments[:, 5], segments[:, 6] = tab[:, 2], 1, K
+    # M = N = 1: the row stride of A and the column stride of B are never used to address a valid element; 0 keeps any padded
+    # row / column the loaders might touch inside the block (a joined slice can exceed the 2^24-element stride limit)
+    segments[:, 0], segments[:, 1], segments[:, 2], segments[:, 3] = K, tab[:, 0], 0, 1
+    segments[:, 4], segments[:, 5], segments[:, 6] = tab[:, 2], 1, 0
     return problems, segments
 
 
