@@ -1,0 +1,42 @@
+"""bench.py contract checks that need no GPU: the reference arm prints ONE JSON line with the keys the driver reads, under
+torchrun-style env only rank 0 prints, and the B200 arm refuses to run without a CUDA device (no CPU fallback)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(args, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + args, capture_output=True, text=True, env=e, timeout=600)
+
+
+def test_reference_arm_prints_one_json_line():
+    r = _run(["--impl", "reference", "--steps", "1", "--warmup", "0", "--sizes", "1024"])
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "block-sparse tensordot GFLOP/s" and d["unit"] == "GFLOP/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["n_gpus"] == 1 and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_reference_arm_other_ranks_stay_silent():
+    r = _run(["--impl", "reference", "--steps", "1", "--warmup", "0", "--sizes", "1024", "--gpus", "2"], env={"RANK": "1", "WORLD_SIZE": "2"})
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_b200_arm_fails_loudly_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("a CUDA device is present")
+    r = _run(["--steps", "1"])
+    assert r.returncode != 0 and r.stdout.strip() == ""
+    assert "no CUDA device" in r.stderr

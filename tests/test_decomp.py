@@ -143,3 +143,18 @@ def test_sector_parallel_svd_many_sectors_cuda():
         for x, y in zip(chk, ref):
             assert torch.equal(x, y)
         assert torch.equal(fns["svdvals"](data, meta, sizes[1]), stock.svdvals(data, meta, sizes[1]))
+
+
+def test_activate_rebinds_and_deactivate_restores_every_function():
+    """Install mode B swaps the five hot functions, vdot and the four decompositions on the stock module and puts the
+    reference's own objects back afterwards."""
+    names = ("transpose_and_merge", "unmerge", "transpose", "dot", "transpose_dot_sum", "vdot", "svd", "svdvals", "eigh", "qr")
+    before = {n: getattr(stock, n) for n in names}
+    yastn_backend.activate()
+    try:
+        assert all(getattr(stock, n) is not before[n] for n in names)
+        assert hasattr(stock, "dot_unmerge") and hasattr(stock, "kernel_tensordot_bs")
+    finally:
+        yastn_backend.deactivate()
+    assert all(getattr(stock, n) is before[n] for n in names)
+    assert not hasattr(stock, "dot_unmerge") and not hasattr(stock, "kernel_tensordot_bs")

@@ -19,7 +19,6 @@ Use with YASTN through ``yastn_b200.yastn_backend`` (``module()`` for ``yastn.ma
 """
 import ctypes
 
-import numpy as np
 import torch
 
 from . import _lib, plans

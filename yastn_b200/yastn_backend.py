@@ -152,7 +152,8 @@ def module(delegate_other_dtypes=True, bs_boundary=False):
 
 
 def activate(delegate_other_dtypes=True):
-    """Install mode B: rebind the five hot functions on ``yastn.backend.backend_torch`` itself."""
+    """Install mode B: rebind the five hot functions, ``vdot`` and the decompositions on ``yastn.backend.backend_torch`` itself
+    (and add ``dot_unmerge`` / ``kernel_tensordot_bs``)."""
     stock = _stock()
     if _state["saved"] is None:
         _state["saved"] = {n: getattr(stock, n) for n in _HOT + ("vdot",)}
@@ -171,6 +172,9 @@ def deactivate():
         for name, fn in _state["saved"].items():
             setattr(stock, name, fn)
         _state["saved"] = None
+        for name in ("dot_unmerge", "kernel_tensordot_bs"):       # added by activate(), not part of the stock module
+            if hasattr(stock, name):
+                delattr(stock, name)
         if _state["saved_decomp"] is not None:
             for name in _DECOMP:
                 setattr(stock, name, getattr(_state["saved_decomp"], name))
