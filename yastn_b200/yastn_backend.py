@@ -5,8 +5,9 @@ YASTN selects its numerics with ``yastn.make_config(backend=<module>)``: a backe
 pass through ``make_config`` untouched (yastn/tensor/_initialize.py:106-115).  Two equivalent install modes:
 
   (A) ``cfg = yastn.make_config(backend=yastn_b200.yastn_backend.module(), default_device='cuda', ...)``
-      — a module object that re-exports the stock torch backend and overrides the five hot functions;
-  (B) ``yastn_b200.yastn_backend.activate()`` — rebinds the five hot functions on
+      — a module object that re-exports the stock torch backend and overrides the five hot functions (plus ``vdot`` and the
+      sector-parallel ``svd`` / ``svdvals`` / ``eigh`` / ``qr`` of yastn_b200.decomp);
+  (B) ``yastn_b200.yastn_backend.activate()`` — rebinds the same functions on
       ``yastn.backend.backend_torch`` in place, after which ``make_config(backend='torch')`` (and the reference's
       unmodified test-suite run with ``--backend torch --device cuda``) drives the B200 kernels.
 
