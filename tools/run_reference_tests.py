@@ -20,7 +20,9 @@ DEFAULT_FILES = ["tensor/test_tensordot.py", "tensor/test_ncon_einsum.py", "tens
                  "tensor/test_tensordot_ad.py", "tensor/test_fuse_meta.py", "tensor/test_cache.py", "mps/test_dmrg.py", "mps/test_env.py",
                  "mps/test_tdvp.py",
                  # decompositions (activate() also installs the sector-parallel svd / qr / eigh of yastn_b200.decomp)
-                 "tensor/test_svd.py", "tensor/test_qr.py", "tensor/test_eigh.py"]
+                 "tensor/test_svd.py", "tensor/test_qr.py", "tensor/test_eigh.py",
+                 # vdot is one grouped-GEMM launch (backend_b200.vdot)
+                 "tensor/test_vdot.py"]
 
 
 class Tally:
