@@ -250,6 +250,57 @@ def test_cpu_tensor_is_rejected_without_shim():
         yastn.tensordot(a, b, axes=((0, 1), (0, 1)))
 
 
+def test_activate_cpu_passthrough_is_opt_in():
+    """After activate() the patched stock module rejects CPU tensors unless cpu_passthrough=True, in which case they go to
+    the functions that were bound before activate() (the reference's code) and are counted as delegated."""
+    cpu_shim.uninstall()
+    try:
+        yastn_backend.activate(cpu_passthrough=True)
+        cfg = yastn.make_config(sym="U1", backend="torch", default_device="cpu")
+        ref = yastn.make_config(sym="U1", backend="np")
+        ref.backend.random_seed(5)
+        a, b = u1_operands(ref, "float64")
+        d0 = yastn_backend.call_counts()["delegated"]["dot"]
+        close(yastn.tensordot(mirror(a, cfg), mirror(b, cfg), axes=((0, 1), (0, 1))), yastn.tensordot(a, b, axes=((0, 1), (0, 1))))
+        assert yastn_backend.call_counts()["delegated"]["dot"] == d0 + 1
+        yastn_backend.deactivate()
+        yastn_backend.activate()
+        with pytest.raises(TypeError, match="no CPU path"):
+            yastn.tensordot(mirror(a, cfg), mirror(b, cfg), axes=((0, 1), (0, 1)))
+    finally:
+        yastn_backend.deactivate()
+
+
+def test_transpose_plan_cache_hits(device):
+    """consume_transpose rebuilds its meta on every call (yastn/tensor/_single.py:343 is not lru-cached): the transpose plan is
+    keyed by content, so repeated transposes of equally structured tensors build ONE plan."""
+    ref, our = cfgs("U1", "fuse_to_matrix", device)
+    ref.backend.random_seed(11)
+    a, _ = u1_operands(ref, "float64")
+    A = mirror(a, our)
+    our.backend.clear_plan_cache()
+    s0 = our.backend.plan_cache_stats()
+    for _ in range(20):
+        close(A.transpose((2, 0, 3, 1)).consume_transpose(), a.transpose((2, 0, 3, 1)).consume_transpose())
+    s1 = our.backend.plan_cache_stats()
+    assert s1["misses"] - s0["misses"] == 1 and s1["hits"] - s0["hits"] == 19 and s1["size"] == 1
+
+
+def test_clear_cache_also_drops_plans(device):
+    """yastn.clear_cache() (yastn/tensor/_control_lru.py:44-63) invalidates every meta the plans are keyed on."""
+    ref, our = cfgs("U1", "fuse_to_matrix", device)
+    ref.backend.random_seed(12)
+    a, b = u1_operands(ref, "float64")
+    A, B = mirror(a, our), mirror(b, our)
+    yastn.tensordot(A, B, axes=((0, 1), (0, 1)))
+    assert our.backend.plan_cache_stats()["size"] > 0
+    yastn.clear_cache()
+    assert our.backend.plan_cache_stats()["size"] == 0
+    close(yastn.tensordot(A, B, axes=((0, 1), (0, 1))), yastn.tensordot(a, b, axes=((0, 1), (0, 1))))
+    yastn.set_cache_maxsize(maxsize=1024)
+    assert our.backend.plan_cache_stats()["size"] == 0
+
+
 def test_dmrg_heisenberg_small(device):
     """Config 1 (reduced): U(1) Heisenberg chain 2-site DMRG runs unmodified on our backend and reproduces the
     energy of the reference numpy backend (reference: tests/mps/test_dmrg.py, yastn/tn/mps/_dmrg.py:42-249)."""

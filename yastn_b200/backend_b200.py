@@ -109,12 +109,14 @@ def _unmerge_plans(data, meta):
 
 
 def _transpose_plans(data, axes, meta):
-    key = ("trn", id(meta), tuple(axes), data.dtype, data.device.index)
+    # consume_transpose (yastn/tensor/_single.py:316-346) is NOT lru-cached: it hands over a fresh, equal meta tuple on
+    # every call, so this plan is keyed by the meta's CONTENT (hash + equality of the nested int tuples), not by identity
+    key = ("trn", meta, tuple(axes), data.dtype, data.device.index)
 
     def build():
         recs, rank = plans.transpose_records(axes, meta)
         return {"fwd": plans.CopyPlan(recs, rank, _ITEMSIZE[data.dtype], data.device.index), "recs": recs, "rank": rank, "bwd": None}
-    return _CACHE.get(key, meta, build)
+    return _CACHE.get(key, None, build)
 
 
 def _bwd_copy_plan(ent, dtype, device):

@@ -525,11 +525,14 @@ class GemmPlan:
 
 
 class PlanCache:
-    """LRU cache of device plans keyed by the *identity* of YASTN's cached meta objects.
+    """LRU cache of device plans.
 
-    YASTN's ``_meta_*`` functions are lru_cached and hand back the same tuple object on every hit
-    (yastn/tensor/_merging.py:137, _contractions.py:281), so ``id(meta)`` is a stable O(1) key; the cache
-    keeps a strong reference to the meta so the id cannot be recycled while the entry lives.
+    Most entries are keyed by the *identity* of YASTN's cached meta objects: the ``_meta_*`` functions behind merge, unmerge,
+    dot and vdot are lru_cached and hand back the same tuple object on every hit (yastn/tensor/_merging.py:137,
+    _contractions.py:281), so ``id(meta)`` is a stable O(1) key; the entry keeps a strong reference to the meta (``anchor``)
+    so the id cannot be recycled while it lives.  Metas that YASTN rebuilds on every call (``consume_transpose``,
+    yastn/tensor/_single.py:343, is not cached) are keyed by content instead: the key holds the meta tuple itself and
+    ``anchor`` is None.
     """
 
     def __init__(self, maxsize=4096):
@@ -540,7 +543,7 @@ class PlanCache:
 
     def get(self, key, anchor, build):
         ent = self._d.get(key)
-        if ent is not None and ent[0] is anchor:
+        if ent is not None and (anchor is None or ent[0] is anchor):
             self._d.move_to_end(key)
             self.hits += 1
             return ent[1]

@@ -30,7 +30,7 @@ from . import decomp as _decomp
 _HOT = _bk.HOT_FUNCTIONS
 _DECOMP = ("svd", "svdvals", "eigh", "qr")
 _NATIVE = (torch.float64, torch.complex128)
-_state = {"module": {}, "saved": None, "saved_f2m": None, "saved_decomp": None,
+_state = {"module": {}, "saved": None, "cpu_passthrough": False, "saved_f2m": None, "saved_decomp": None,
           "calls": {name: 0 for name in _HOT + ("dot_unmerge", "kernel_tensordot_bs", "vdot")}, "delegated": {name: 0 for name in _HOT}}
 
 
@@ -44,8 +44,12 @@ def _stock():
 
 
 def _native(*tensors):
+    """True: float64 / complex128 CUDA tensors (our kernels).  False: the call is handed to the reference's own torch code
+    (other dtypes; CPU tensors only when the stock module was patched with ``activate(cpu_passthrough=True)``)."""
     for t in tensors:
         if not t.is_cuda:
+            if _state["cpu_passthrough"]:
+                return False
             raise TypeError(f"yastn_b200: CPU tensor reached a hot backend function (device {t.device}); "
                             "this backend has no CPU path — build the config with default_device='cuda'")
     return all(t.dtype in _NATIVE for t in tensors)
@@ -56,7 +60,7 @@ def _make_hot(stock_fns, delegate):
     calls, delegated = _state["calls"], _state["delegated"]
 
     def other(name, *args):
-        if not delegate:
+        if not delegate and all(t.is_cuda for t in args if isinstance(t, torch.Tensor)):
             raise TypeError(f"yastn_b200.{name}: dtype not float64/complex128 and delegate_other_dtypes=False")
         delegated[name] += 1
         return stock_fns[name](*args)
@@ -119,6 +123,34 @@ def _make_hot(stock_fns, delegate):
             "vdot": vdot}
 
 
+def _hook_cache_control():
+    """``yastn.clear_cache()`` / ``yastn.set_cache_maxsize()`` (yastn/tensor/_control_lru.py:22-63) drop or re-wrap YASTN's
+    lru-cached ``_meta_*`` functions; the device plans keyed on the identity of those metas can never be hit again, so the
+    same calls also empty the plan cache (their tables go back to the device pool)."""
+    if _state.get("lru_hooked"):
+        return
+    import sys
+    import yastn
+    ctl = sys.modules.get("yastn.tensor._control_lru")
+    if ctl is None:
+        return
+    saved = {n: getattr(ctl, n) for n in ("clear_cache", "set_cache_maxsize")}
+
+    def clear_cache():
+        saved["clear_cache"]()
+        _bk.clear_plan_cache()
+
+    def set_cache_maxsize(maxsize=0):
+        saved["set_cache_maxsize"](maxsize)
+        _bk.clear_plan_cache()
+    clear_cache.__doc__, set_cache_maxsize.__doc__ = saved["clear_cache"].__doc__, saved["set_cache_maxsize"].__doc__
+    for mod in (ctl, sys.modules.get("yastn.tensor"), yastn):
+        for name, fn in (("clear_cache", clear_cache), ("set_cache_maxsize", set_cache_maxsize)):
+            if mod is not None and getattr(mod, name, None) is saved[name]:
+                setattr(mod, name, fn)
+    _state["lru_hooked"] = True
+
+
 def _make_decomp(stock):
     """Sector-parallel svd / svdvals / eigh / qr (yastn_b200.decomp) on top of the reference's own implementations."""
     if _state["saved_decomp"] is None:
@@ -132,11 +164,12 @@ def module(delegate_other_dtypes=True, bs_boundary=False):
 
     ``bs_boundary=True`` returns the variant whose ``BACKEND_ID`` is ``"torch_cpp"``: YASTN then routes ``no_fusion``
     contractions through the single-call ``kernel_tensordot_bs`` boundary (yastn/tensor/_contractions.py:199-242)."""
-    variant = bool(bs_boundary)
+    variant = (bool(bs_boundary), bool(delegate_other_dtypes))
     if variant not in _state["module"]:
         stock = _stock()
+        _hook_cache_control()
         saved = _state["saved"] or {n: getattr(stock, n) for n in _HOT + ("vdot",)}
-        mod = types.ModuleType("yastn_b200_backend" + ("_bs" if variant else ""),
+        mod = types.ModuleType("yastn_b200_backend" + ("_bs" if bs_boundary else ""),
                                "stock yastn torch backend with the B200 contraction kernels")
         for name in dir(stock):
             if not name.startswith("__"):
@@ -145,17 +178,24 @@ def module(delegate_other_dtypes=True, bs_boundary=False):
             setattr(mod, name, fn)
         for name, fn in _make_decomp(stock).items():
             setattr(mod, name, fn)
-        mod.BACKEND_ID = "torch_cpp" if variant else "torch"
+        mod.BACKEND_ID = "torch_cpp" if bs_boundary else "torch"
         mod.clear_plan_cache = _bk.clear_plan_cache
         mod.plan_cache_stats = _bk.plan_cache_stats
         _state["module"][variant] = mod
     return _state["module"][variant]
 
 
-def activate(delegate_other_dtypes=True):
+def activate(delegate_other_dtypes=True, cpu_passthrough=False):
     """Install mode B: rebind the five hot functions, ``vdot`` and the decompositions on ``yastn.backend.backend_torch`` itself
-    (and add ``dot_unmerge`` / ``kernel_tensordot_bs``)."""
+    (and add ``dot_unmerge`` / ``kernel_tensordot_bs``).
+
+    ``activate`` patches the process-wide stock module, so configs built with ``backend='torch'`` on the CPU would reach our
+    functions too.  By default that raises (this backend has no CPU path and never pretends to); with
+    ``cpu_passthrough=True`` CPU tensors are handed back to the functions that were bound on the stock module before
+    ``activate`` — the reference's own code, counted under ``call_counts()['delegated']``."""
     stock = _stock()
+    _hook_cache_control()
+    _state["cpu_passthrough"] = bool(cpu_passthrough)
     if _state["saved"] is None:
         _state["saved"] = {n: getattr(stock, n) for n in _HOT + ("vdot",)}
     for name, fn in _make_hot(_state["saved"], delegate_other_dtypes).items():
@@ -168,6 +208,7 @@ def activate(delegate_other_dtypes=True):
 
 def deactivate():
     """Undo :func:`activate`."""
+    _state["cpu_passthrough"] = False
     if _state["saved"] is not None:
         stock = _stock()
         for name, fn in _state["saved"].items():
