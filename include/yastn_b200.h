@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define YB_ABI_VERSION 1
+#define YB_ABI_VERSION 2
 
 /* element types */
 #define YB_F64 0
@@ -82,8 +82,13 @@ int yb_gemm_plan_create_scatter(const int64_t* problems, int64_t nprob, const in
                                 const int64_t* col_ptr, const int64_t* col_cuts, const int64_t* dst_ptr, const int64_t* dst,
                                 int dtype, int device, yb_gemm_plan** out);
 /* info[0]=tiles, [1]=real multiply-adds (M*N*K summed), [2]=big tiles, [3]=small tiles, [4]=grid (CTAs), [5]=CTAs that
- * start inside a tile (stream-K partials).  Plans of one device share a stream-K workspace: run them on one stream at a time. */
-int yb_gemm_plan_info(const yb_gemm_plan* plan, int64_t info[6]);
+ * start inside a tile (stream-K partials), [6]=warps of the skinny-output kernel, [7]=its partial-sum runs.
+ * Problems whose result block is at most 8 x 8 (complex128: at most 32 entries) are not tiled: they run as HBM-bound
+ * reductions over the contraction index in a second kernel of the same yb_gemm_run call (backend.vdot, huge-K / tiny-output
+ * contractions, adjoints of tall-and-skinny products); any strides are accepted for them.
+ * Cross-CTA scratch (stream-K partial tiles, partial sums) is looked up per (device, stream) at launch time: plans may run
+ * concurrently on different streams.  Launches that wait on partial tiles of other CTAs are cooperative launches. */
+int yb_gemm_plan_info(const yb_gemm_plan* plan, int64_t info[8]);
 int yb_gemm_run(const yb_gemm_plan* plan, const void* A, const void* B, void* C, int flags, void* stream);
 void yb_gemm_plan_destroy(yb_gemm_plan* plan);
 

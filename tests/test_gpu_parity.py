@@ -288,16 +288,17 @@ def test_fused_dot_unmerge_matches_two_calls(bk, name, dtype):
     assert torch.equal(A1.grad, A2.grad) and torch.equal(B1.grad, B2.grad)
 
 
-def test_stream_k_is_deterministic_and_splits(bk):
-    """Huge-K / tiny-output contraction (pattern P3): the k-range of a tile is shared by many CTAs (stream-K); partials are
-    added in fixed CTA order, so repeated runs are bit-identical, and the result matches a per-sector torch.matmul."""
+def test_p3_runs_on_the_skinny_path_and_is_deterministic(bk):
+    """Huge-K / tiny-output contraction (pattern P3): the contraction index is shared out over thousands of warps of the
+    skinny kernel (no DMMA tiles at all); partial sums are added in fixed run order, so repeated runs are bit-identical, and the
+    result matches a per-sector torch.matmul.  (Stream-K on tiles: tests/test_gpu_skinny.py::test_stream_k_still_splits...)"""
     from yastn_b200 import plans as _plans
     case = bench_structs()["U1_D2048_P3"]
     st = case["f2m"]
     md = st["dot"]["meta_dot"]
     problems, segments = _plans.dot_tables(md)
     info = _plans.GemmPlan(problems, segments, 0, torch.cuda.current_device()).info()
-    assert info["split_ctas"] > 100 and info["grid"] > 100      # 3 tiny output blocks spread over the whole GPU
+    assert info["tiles"] == 0 and info["skinny_warps"] > 100 and info["skinny_runs"] >= info["skinny_warps"]   # 3 tiny blocks, whole GPU
     gen = torch.Generator(device="cuda").manual_seed(5)
     na = max(r[2][1] for r in md); nb = max(r[4][1] for r in md)
     A = torch.rand(na, dtype=torch.float64, device="cuda", generator=gen) * 2 - 1

@@ -119,7 +119,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"libyastn_b200.so does not export {name}"
     assert declared == set(_lib.SIGNATURES), "ctypes signature table out of sync with the header"
-    assert lib.yb_abi_version() == 1
+    assert lib.yb_abi_version() == _lib.ABI_VERSION
 
 
 def test_unmerge_scatter_tables():

@@ -33,6 +33,7 @@ SIGNATURES = {
     "yb_match_sectors": (_c.c_int, [_vp, _vp, _vp, _c.c_int64, _vp, _vp, _vp, _c.c_int64, _c.c_int, _c.c_int64, _vp, _vp, _vp, _vp, _vp]),
 }
 
+ABI_VERSION = 2
 YB_F64, YB_C128 = 0, 1
 YB_COPY_ZERO_DST, YB_COPY_CONJ = 1, 2
 YB_GEMM_CONJ_A, YB_GEMM_CONJ_B = 1, 2
@@ -52,7 +53,7 @@ def load():
             fn = getattr(lib, name)  # AttributeError if the symbol is missing
             fn.restype = res
             fn.argtypes = args
-        if lib.yb_abi_version() != 1:
+        if lib.yb_abi_version() != ABI_VERSION:
             raise ImportError("libyastn_b200.so ABI version mismatch; rebuild")
         _lib = lib
     return _lib

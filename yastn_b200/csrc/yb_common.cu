@@ -1,5 +1,7 @@
 #include "yb_common.h"
 
+#include <algorithm>
+#include <map>
 #include <mutex>
 
 namespace yb {
@@ -78,6 +80,89 @@ int pool_upload(int device, void* dst, const void* host, size_t bytes) {
     YB_CUDA(cudaMemcpyAsync(dst, host, bytes, cudaMemcpyHostToDevice, p.copy_stream));
     YB_CUDA(cudaEventRecord(p.copy_done, p.copy_stream));
     YB_CUDA(cudaEventSynchronize(p.copy_done));   // the host waits for this copy only, not for the compute streams
+    return kOk;
+}
+
+namespace {
+struct StreamWs {
+    void* ws = nullptr;
+    int* flags = nullptr;
+    size_t ws_bytes = 0, nflags = 0;
+};
+constexpr size_t kWsDefaultBytes = 32u << 20;     // stream-K: 296 slots x 64 KB = 18.5 MiB; skinny partials: 0.5..1 KB per run
+constexpr size_t kWsDefaultFlags = 1u << 16;
+std::mutex ws_mu;
+std::map<std::pair<int, cudaStream_t>, StreamWs> ws_table;
+std::vector<StreamWs> ws_spare[64];
+
+// cudaMalloc + zeroed flags, without touching any caller stream (the pool's copy stream, host-synchronised)
+int ws_alloc(int device, size_t ws_bytes, size_t nflags, StreamWs* out) {
+    StreamWs e;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    if (prev != device) YB_CUDA(cudaSetDevice(device));
+    cudaError_t err = cudaMalloc(&e.ws, ws_bytes);
+    if (err == cudaSuccess) err = cudaMalloc((void**)&e.flags, nflags * sizeof(int));
+    if (err == cudaSuccess) {
+        DevicePool& pool = pool_of(device);
+        std::lock_guard<std::mutex> lk(pool.mu);
+        if (!pool.copy_stream) {
+            err = cudaStreamCreateWithFlags(&pool.copy_stream, cudaStreamNonBlocking);
+            if (err == cudaSuccess) err = cudaEventCreateWithFlags(&pool.copy_done, cudaEventDisableTiming);
+        }
+        if (err == cudaSuccess) err = cudaMemsetAsync(e.flags, 0, nflags * sizeof(int), pool.copy_stream);
+        if (err == cudaSuccess) err = cudaEventRecord(pool.copy_done, pool.copy_stream);
+        if (err == cudaSuccess) err = cudaEventSynchronize(pool.copy_done);
+    }
+    if (prev != device) cudaSetDevice(prev);
+    if (err != cudaSuccess) {
+        cudaGetLastError();
+        return fail(kErrCuda, "yastn_b200: allocating a %zu-byte reduction workspace failed: %s (a stream that is being captured into "
+                    "a CUDA graph cannot allocate: run the call once on that stream before capturing)", ws_bytes, cudaGetErrorString(err));
+    }
+    e.ws_bytes = ws_bytes;
+    e.nflags = nflags;
+    *out = e;
+    return kOk;
+}
+}  // namespace
+
+int workspace_reserve(int device) {
+    if (device < 0 || device >= 64) return fail(kErrArg, "yastn_b200: device index %d out of range", device);
+    std::lock_guard<std::mutex> lk(ws_mu);
+    if (!ws_spare[device].empty()) return kOk;
+    StreamWs e;
+    int rc = ws_alloc(device, kWsDefaultBytes, kWsDefaultFlags, &e);
+    if (rc != kOk) return rc;
+    ws_spare[device].push_back(e);
+    return kOk;
+}
+
+int stream_workspace(int device, cudaStream_t st, size_t ws_bytes, size_t nflags, void** ws, int** flags) {
+    if (device < 0 || device >= 64) return fail(kErrArg, "yastn_b200: device index %d out of range", device);
+    std::lock_guard<std::mutex> lk(ws_mu);
+    auto it = ws_table.find({device, st});
+    if (it == ws_table.end()) {
+        StreamWs e;
+        if (!ws_spare[device].empty() && ws_spare[device].back().ws_bytes >= ws_bytes && ws_spare[device].back().nflags >= nflags) {
+            e = ws_spare[device].back();     // a stream seen for the first time (e.g. torch's graph-capture stream): no allocation
+            ws_spare[device].pop_back();
+        } else {
+            int rc = ws_alloc(device, std::max(ws_bytes, kWsDefaultBytes), std::max(nflags, kWsDefaultFlags), &e);
+            if (rc != kOk) return rc;
+        }
+        it = ws_table.emplace(std::make_pair(device, st), e).first;
+    }
+    StreamWs& e = it->second;
+    if (e.ws_bytes < ws_bytes || e.nflags < nflags) {
+        // grow: the old buffers stay allocated (kernels already queued, or captured in a graph, still use them)
+        StreamWs g;
+        int rc = ws_alloc(device, std::max(ws_bytes, 2 * e.ws_bytes), std::max(nflags, 2 * e.nflags), &g);
+        if (rc != kOk) return rc;
+        e = g;
+    }
+    *ws = e.ws;
+    *flags = e.flags;
     return kOk;
 }
 

@@ -32,6 +32,15 @@ int pool_alloc(int device, size_t bytes, void** ptr, size_t* cap);
 void pool_free(int device, void* ptr, size_t cap);
 int pool_upload(int device, void* dst, const void* host, size_t bytes);
 
+// Scratch of the kernels that reduce across CTAs (stream-K partial tiles, skinny partial sums): one buffer per
+// (device, stream), looked up at launch time and grown on demand, so launches on different streams never share slots.
+// `flags` are zero when handed out for the first time and every kernel leaves them at zero.  A buffer that has been
+// handed out is never freed (queued kernels and captured CUDA graphs keep using it); growth at least doubles it.
+int stream_workspace(int device, cudaStream_t st, size_t ws_bytes, size_t nflags, void** ws, int** flags);
+// Called when a plan that needs a workspace is created: keeps one spare default-sized workspace per device, so that the first
+// launch on a stream never seen before — torch's CUDA-graph capture stream, where cudaMalloc is not allowed — finds one.
+int workspace_reserve(int device);
+
 // Owns one device allocation holding a host-built table (the current device must be the plan's device).
 struct DeviceTable {
     void* ptr = nullptr;

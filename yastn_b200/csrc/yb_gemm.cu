@@ -23,7 +23,7 @@
 #include <cmath>
 #include <type_traits>
 
-#include "yb_common.h"
+#include "yb_gemm_types.h"
 
 namespace yb {
 
@@ -32,21 +32,6 @@ constexpr int kStages = 4;
 constexpr int kRowBytes = 128;      // bytes of one K-row (KC format): 16 doubles or 8 complex
 constexpr int kTilesInFlight = 296;   // resident CTAs of a full launch (148 SMs x 2): sizes the L2 tile bands
 constexpr int kWsDoubles = 64 * kGemmThreads;   // partial-accumulator slot per CTA (64 doubles per thread)
-
-struct GemmProblem {
-    int32_t M, N;
-    int32_t seg_begin, seg_end;
-    int64_t offC, ldc;
-    int32_t scat;      // index into the scatter table, -1: plain row-major store at offC / ldc
-    int32_t pad_;
-};
-
-struct GemmSegment {
-    int64_t offA, offB;
-    int64_t sAm, sAk, sBk, sBn;
-    int32_t K;
-    int32_t align;  // bit0: A rows 16B-aligned, bit1: B rows 16B-aligned (relative to a 16B-aligned base pointer)
-};
 
 struct GemmTile {
     int32_t prob, m0, n0, cfg;   // cfg 0: big tile, 1: small tile
@@ -58,14 +43,6 @@ struct GemmTile {
 // before k-iteration it_end of the last one.
 struct CtaRange {
     int32_t tile_begin, it_begin, tile_end, it_end;
-};
-
-// Fused unmerge: element (r, c) of the merged block goes to  dst[rowinfo[r].x * ncs + colinfo[c].x]
-//                                                            + rowinfo[r].y * colinfo[c].z + colinfo[c].y
-struct ScatterInfo {
-    int64_t dst_off;             // into the int64 pool of destination block offsets (nrs x ncs)
-    int32_t row_off, col_off;    // into the int2 (row) / int4 (col) pools
-    int32_t ncs, pad_;
 };
 
 struct GemmArgs {
@@ -506,38 +483,12 @@ struct yb_gemm_plan {
     int ntiles = 0, grid = 0, nsplit = 0;
     int64_t macs = 0, nbig = 0, nsmall = 0;
     DeviceTable problems, segments, tiles, ranges, scat, rowinfo, colinfo, dstpool;
-    double* ws = nullptr;   // per-device stream-K workspace (shared by all plans of the device, see device_workspace)
-    int* flags = nullptr;
+    int ws_slots = 0;       // stream-K partial-tile slots this plan needs (0: no CTA starts inside a tile)
+    bool cooperative = false;
+    SkinnyPlan* skinny = nullptr;   // problems with a tiny result block and a long contraction index (yb_skinny.cu)
 };
 
 namespace {
-
-// Stream-K workspace: one partial-tile slot and one flag per resident CTA.  It is shared by every plan of a
-// device (a plan cache holds thousands of plans), which is safe because launches of one device are stream-ordered
-// by the caller (YASTN runs on torch's current stream) and every launch leaves all flags at 0.
-struct DeviceWorkspace {
-    double* ws = nullptr;
-    int* flags = nullptr;
-    int slots = 0;
-};
-int device_workspace(int device, int slots, DeviceWorkspace** out) {
-    static DeviceWorkspace table[64];
-    if (device < 0 || device >= 64) return fail(kErrArg, "yb_gemm: device index %d out of range", device);
-    DeviceWorkspace& w = table[device];
-    if (w.slots < slots) {
-        if (w.ws) cudaFree(w.ws);
-        if (w.flags) cudaFree(w.flags);
-        w.ws = nullptr;
-        w.flags = nullptr;
-        w.slots = 0;
-        YB_CUDA(cudaMalloc(&w.ws, (size_t)slots * kWsDoubles * sizeof(double)));
-        YB_CUDA(cudaMalloc(&w.flags, (size_t)slots * sizeof(int)));
-        YB_CUDA(cudaMemset(w.flags, 0, (size_t)slots * sizeof(int)));
-        w.slots = slots;
-    }
-    *out = &w;
-    return kOk;
-}
 
 template <bool CPLX, int AL, int BL>
 int occupancy(int device, int* blocks_per_sm) {
@@ -564,7 +515,15 @@ int occupancy_layout(int al, int bl, int device, int* b) {
 template <bool CPLX, int AL, int BL>
 int launch(const yb_gemm_plan* p, const GemmArgs& args, cudaStream_t st) {
     using G = GroupKernel<CPLX, AL, BL>;
-    gemm_kernel<CPLX, AL, BL><<<p->grid, kGemmThreads, G::SMEM_BYTES, st>>>(args);
+    if (p->cooperative) {
+        // CTAs that finish a split tile wait for the partials of other CTAs: a cooperative launch makes the driver
+        // guarantee that the whole grid (<= SMs x occupancy) is resident at once, whatever else runs on the device
+        void* kargs[] = {(void*)&args};
+        YB_CUDA(cudaLaunchCooperativeKernel((const void*)gemm_kernel<CPLX, AL, BL>, dim3(p->grid), dim3(kGemmThreads), kargs,
+                                            (size_t)G::SMEM_BYTES, st));
+    } else {
+        gemm_kernel<CPLX, AL, BL><<<p->grid, kGemmThreads, G::SMEM_BYTES, st>>>(args);
+    }
     YB_CUDA(cudaGetLastError());
     return kOk;
 }
@@ -622,6 +581,49 @@ int create_plan(const int64_t* problems, int64_t nprob, const int64_t* segments,
             if (scat_index[i] < -1 || scat_index[i] >= nscat) return fail(kErrArg, "yb_gemm_plan_create: problem %lld scatter index", (long long)i);
             g.scat = (int32_t)scat_index[i];
         }
+    }
+
+    // ---- routing: tiny result blocks with a long contraction index are reductions, not tiles (yb_skinny.cu) -----------
+    std::vector<char> is_skinny((size_t)nprob, 0);
+    std::vector<int> skinny_set;
+    {
+        auto p2 = [](int v) { int p = 1; while (p < v) p <<= 1; return p; };
+        auto ksum = [&](const GemmProblem& g) {
+            int64_t k = 0;
+            for (int s = g.seg_begin; s < g.seg_end; ++s) k += hs[(size_t)s].K;
+            return k;
+        };
+        int lim = kSkinnyMax;
+        for (int pass = 0; pass < 2; ++pass) {
+            skinny_set.clear();
+            bool all = true;
+            int mx = 1, nx = 1;
+            for (int64_t i = 0; i < nprob; ++i) {
+                const GemmProblem& g = hp[(size_t)i];
+                if (g.M == 0 || g.N == 0) continue;
+                if (g.M <= lim && g.N <= lim && p2(g.M) * p2(g.N) <= skinny_entries(cplx)) {
+                    skinny_set.push_back((int)i);
+                    mx = std::max(mx, (int)g.M);
+                    nx = std::max(nx, (int)g.N);
+                } else {
+                    all = false;
+                }
+            }
+            if (!all) {   // mixed plan: a second launch only pays for long contractions
+                std::vector<int> keep;
+                for (int i : skinny_set)
+                    if (ksum(hp[(size_t)i]) >= 2048) keep.push_back(i);
+                skinny_set.swap(keep);
+            }
+            if (p2(mx) * p2(nx) <= skinny_entries(cplx)) break;
+            lim = 4;      // complex128: 8 x 2 and 2 x 8 blocks in one plan would need 8 x 8 accumulators per lane
+        }
+        for (int i : skinny_set) is_skinny[(size_t)i] = 1;
+    }
+
+    for (int64_t i = 0; i < nprob; ++i) {
+        const GemmProblem& g = hp[(size_t)i];
+        if (is_skinny[(size_t)i]) continue;    // the skinny kernel takes any strides
         // layout feasibility: a layout is usable when its contiguous index has unit stride (or extent <= 1)
         for (int s = g.seg_begin; s < g.seg_end; ++s) {
             const GemmSegment& sg = hs[(size_t)s];
@@ -700,7 +702,7 @@ int create_plan(const int64_t* problems, int64_t nprob, const int64_t* segments,
     auto tile_weight = [](const GemmTile& t) { return std::max<int64_t>(t.iters, 1) * (t.cfg == 0 ? 2 : 1); };
     for (int64_t i = 0; i < nprob; ++i) {
         const GemmProblem& g = hp[(size_t)i];
-        if (g.M == 0 || g.N == 0) continue;
+        if (g.M == 0 || g.N == 0 || is_skinny[(size_t)i]) continue;
         int64_t ksum = 0, iters = 0;
         for (int s = g.seg_begin; s < g.seg_end; ++s) {
             ksum += hs[(size_t)s].K;
@@ -736,6 +738,11 @@ int create_plan(const int64_t* problems, int64_t nprob, const int64_t* segments,
         }
         W += count * tile_weight(proto);
         (big ? nbig : nsmall) += count;
+    }
+
+    for (int i : skinny_set) {
+        const GemmProblem& g = hp[(size_t)i];
+        for (int s = g.seg_begin; s < g.seg_end; ++s) macs += (int64_t)g.M * g.N * hs[(size_t)s].K;
     }
 
     yb_gemm_plan* plan = new yb_gemm_plan();
@@ -828,13 +835,13 @@ int create_plan(const int64_t* problems, int64_t nprob, const int64_t* segments,
     if (rc == kOk) rc = plan->colinfo.upload(hcol.data(), hcol.size() * sizeof(int4));
     if (rc == kOk) rc = plan->dstpool.upload(hdst.data(), hdst.size() * sizeof(int64_t));
     if (rc == kOk && plan->nsplit > 0) {
-        DeviceWorkspace* w = nullptr;
-        rc = device_workspace(device, max_grid, &w);
-        if (rc == kOk) {
-            plan->ws = w->ws;
-            plan->flags = w->flags;
-        }
+        plan->ws_slots = max_grid;
+        int coop = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+        plan->cooperative = coop != 0;
     }
+    if (rc == kOk && !skinny_set.empty()) rc = skinny_create(hp, hs, skinny_set, cplx, device, &plan->skinny);
+    if (rc == kOk && (plan->ws_slots > 0 || plan->skinny)) rc = workspace_reserve(device);
     cudaSetDevice(prev);
     if (rc != kOk) {
         yb_gemm_plan_destroy(plan);
@@ -861,7 +868,7 @@ extern "C" int yb_gemm_plan_create_scatter(const int64_t* problems, int64_t npro
     return create_plan(problems, nprob, segments, nseg, scat_index, nscat, row_ptr, row_cuts, col_ptr, col_cuts, dst_ptr, dst, dtype, device, out);
 }
 
-extern "C" int yb_gemm_plan_info(const yb_gemm_plan* plan, int64_t info[6]) {
+extern "C" int yb_gemm_plan_info(const yb_gemm_plan* plan, int64_t info[8]) {
     if (!plan || !info) return fail(kErrArg, "yb_gemm_plan_info: null argument");
     info[0] = plan->ntiles;
     info[1] = plan->macs;
@@ -869,13 +876,25 @@ extern "C" int yb_gemm_plan_info(const yb_gemm_plan* plan, int64_t info[6]) {
     info[3] = plan->nsmall;
     info[4] = plan->grid;
     info[5] = plan->nsplit;
+    skinny_info(plan->skinny, &info[6], &info[7]);
     return kOk;
 }
 
 extern "C" int yb_gemm_run(const yb_gemm_plan* plan, const void* A, const void* B, void* C, int flags, void* stream) {
     if (!plan) return fail(kErrArg, "yb_gemm_run: plan is null");
-    if (plan->ntiles == 0) return kOk;
+    if (plan->ntiles == 0 && !plan->skinny) return kOk;
     if (!A || !B || !C) return fail(kErrArg, "yb_gemm_run: null data pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (plan->dtype == YB_C128 && ((((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15) != 0))
+        return fail(kErrArg, "yb_gemm_run: complex128 operands must be 16-byte aligned");
+    if (plan->skinny) {
+        ScatterTables sc = {(const ScatterInfo*)plan->scat.ptr, (const int2*)plan->rowinfo.ptr, (const int4*)plan->colinfo.ptr,
+                            (const int64_t*)plan->dstpool.ptr};
+        int rc = skinny_run(plan->skinny, (const GemmProblem*)plan->problems.ptr, (const GemmSegment*)plan->segments.ptr, sc, A, B, C,
+                            flags, st);
+        if (rc != kOk) return rc;
+    }
+    if (plan->ntiles == 0) return kOk;
     GemmArgs args;
     args.problems = (const GemmProblem*)plan->problems.ptr;
     args.segs = (const GemmSegment*)plan->segments.ptr;
@@ -885,18 +904,21 @@ extern "C" int yb_gemm_run(const yb_gemm_plan* plan, const void* A, const void* 
     args.rowinfo = (const int2*)plan->rowinfo.ptr;
     args.colinfo = (const int4*)plan->colinfo.ptr;
     args.dstpool = (const int64_t*)plan->dstpool.ptr;
-    args.ws = plan->ws;
-    args.sync_flags = plan->flags;
+    args.ws = nullptr;
+    args.sync_flags = nullptr;
+    if (plan->ws_slots > 0) {   // looked up per launch: one workspace per (device, stream), never shared between streams
+        void* ws = nullptr;
+        int rc = stream_workspace(plan->device, st, (size_t)plan->ws_slots * kWsDoubles * sizeof(double), (size_t)plan->ws_slots, &ws,
+                                  &args.sync_flags);
+        if (rc != kOk) return rc;
+        args.ws = (double*)ws;
+    }
     args.A = (const char*)A;
     args.B = (const char*)B;
     args.C = (char*)C;
     args.flags = flags;
     args.base_aligned = (((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15) == 0;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (plan->dtype == YB_C128) {
-        if (!args.base_aligned) return fail(kErrArg, "yb_gemm_run: complex128 operands must be 16-byte aligned");
-        return dispatch_layout<true>(plan, args, st);
-    }
+    if (plan->dtype == YB_C128) return dispatch_layout<true>(plan, args, st);
     return dispatch_layout<false>(plan, args, st);
 }
 
@@ -910,5 +932,6 @@ extern "C" void yb_gemm_plan_destroy(yb_gemm_plan* plan) {
     plan->rowinfo.release();
     plan->colinfo.release();
     plan->dstpool.release();
+    skinny_destroy(plan->skinny);
     delete plan;
 }
