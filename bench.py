@@ -5,7 +5,8 @@
 
 Workload (SURVEY.md 8d "config 5"): synthetic U(1) rank-4 tensors A[L*,p,p,L], F[L*,w,L], B4[L*,p*,p*,L] with
 gaussian-distributed sector dimensions, total leg dimension D in {1024, 2048, 4096, 8192, 16384} (7..47 charge
-sectors, 24..184 blocks), contractions P1 = tensordot(A, F, (3, 0)) and P2 = tensordot(A, B4, ((1,2,3),(2,1,0))).
+sectors, 24..184 blocks), contractions P1 = tensordot(A, F, (3, 0)), P2 = tensordot(A, B4, ((1,2,3),(2,1,0))) and
+P3 = tensordot(A.transpose((2,0,3,1)), B4, ((1,2),(3,0))) (both big legs contracted: K ~ 1e7, result blocks <= 4 x 4).
 The block structure and all backend metas come from the reference (tests/golden/structs_bench.json.gz, recorded
 from yastn's own _meta_* functions); data is uniform(-1, 1) generated at run time.  One "step" is one pass over
 the whole sweep (every size x pattern: merge A, merge B, grouped GEMM, unmerge).  Inputs exceed L2 (126 MB) for
@@ -18,6 +19,14 @@ e2e    = same metric through the backend API with HOST (pinned) operands: H2D of
 N > 1  = the charge sectors of every contraction are sharded FLOP-balanced over the ranks (no collective on
          the data path); value = total FLOPs / max-over-ranks time ("strong" scaling).  In the e2e leg every rank moves
          only the operand blocks its sectors read and the result blocks it writes; the byte counts are job totals.
+--impl reference = the UNMODIFIED reference (yastn from baseline/_ref, numpy backend, OpenBLAS on all host cores) running
+         yastn.tensordot on the SAME sizes, patterns and dtype: tensors built with the same recipe the golden structures were
+         recorded from (tests/golden/make_golden.py), every step one full pass.
+gpu_baseline = the reference's stock torch backend on the same GPU (loop of cuBLAS calls and slice copies,
+         yastn/backend/_backend_torch_backwards.py:100-109,340-364,397-408) through yastn.tensordot, and our backend module
+         through the very same yastn.tensordot calls.
+dmrg_sweep_s = one 2-site DMRG sweep of the U(1)xU(1) Hubbard chain at D=4096 complex128 (BASELINE config 3 shape, N=20 sites)
+         on the unmodified YASTN with our backend module and with the stock torch backend on the same GPU.
 """
 import argparse
 import json
@@ -26,6 +35,11 @@ import subprocess
 import sys
 import threading
 import time
+
+if "reference" in sys.argv[1:]:
+    # the reference arm uses every host core: torchrun exports OMP_NUM_THREADS=1 to its ranks, which would throttle OpenBLAS
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count())
 
 import numpy as np
 
@@ -41,7 +55,8 @@ try:
 except Exception:
     HBM_PEAK_GBS, HBM_FROM_FILE = 6650.0, False
 DEFAULT_SIZES = (1024, 2048, 4096, 8192, 16384)
-PATTERNS = ("P1", "P2")
+PATTERNS = ("P1", "P2", "P3")
+SIGMA = {64: 0.7, 1024: 1.0, 2048: 1.5, 4096: 2.5, 8192: 4.0, 16384: 6.0}    # gaussian_leg widths of the recorded structures
 
 
 def load_cases(sizes):
@@ -111,34 +126,102 @@ class ClockSampler:
 
 
 # -------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port (numpy + OpenBLAS) on the host cores
+# reference arm / cpu baseline / gpu baseline: the unmodified reference (baseline/_ref) through yastn.tensordot
 # -------------------------------------------------------------------------------------------------
 
-def cpu_time_cases(cases, cplx, reps):
+def workload_config(sizes, world):
+    """The `config` object of the JSON line; identical for both arms (same workload, same sizes)."""
+    cases = load_cases(tuple(sizes))
+    return {"workload": f"synthetic U(1) rank-4 block-sparse tensordot sweep (SURVEY 8d config 5): D={list(sizes)}, "
+                        f"P1=A.F axes (3,0), P2=A.B4 axes ((1,2,3),(2,1,0)), P3=A^T.B4 axes ((1,2),(3,0)); fuse_to_matrix policy "
+                        f"(merge, merge, sector GEMMs, unmerge)",
+            "contractions_per_step": len(cases),
+            "l2": "operands + results of one step (>10 GB) exceed L2 and the host caches; no flush needed",
+            "sharding": "charge sectors FLOP-balanced over ranks, no collective" if world > 1 else "single GPU"}
+
+
+def load_reference():
+    from yastn_loader import load_yastn
+    return load_yastn(allow_reference_checkout=False)
+
+
+def yastn_workload(yastn, cfg, sizes, cplx):
+    """The synthetic tensors of the sweep built by the reference itself (recipe of SURVEY 8d = tests/golden/make_golden.py:
+    gaussian_leg + rand); returns [(name, a, b, axes)] in the order of load_cases()."""
+    dtype = "complex128" if cplx else "float64"
+    cfg.backend.random_seed(0)
+    out = []
+    for D in sizes:
+        L = yastn.gaussian_leg(cfg, s=1, n=0, sigma=SIGMA[D], D_total=D, method="round")
+        p = yastn.Leg(cfg, s=1, t=(-1, 1), D=(1, 1))
+        w = yastn.Leg(cfg, s=1, t=(-2, 0, 2), D=(1, 3, 1))
+        A = yastn.rand(cfg, legs=[L.conj(), p, p, L], n=0, dtype=dtype)
+        F = yastn.rand(cfg, legs=[L.conj(), w, L], n=0, dtype=dtype)
+        B4 = yastn.rand(cfg, legs=[L.conj(), p.conj(), p.conj(), L], n=0, dtype=dtype)
+        ops = {"P1": (A, F, (3, 0)), "P2": (A, B4, ((1, 2, 3), (2, 1, 0))), "P3": (A.transpose((2, 0, 3, 1)), B4, ((1, 2), (3, 0)))}
+        for pat in PATTERNS:
+            out.append((f"U1_D{D}_{pat}",) + ops[pat])
+    return out
+
+
+def check_same_structure(work, cases):
+    """The tensors the reference built have exactly the recorded block structure (same config on both arms)."""
+    for (name, a, b, _), (cname, case) in zip(work, cases):
+        assert name == cname and a.size == case["a"]["size"] and b.size == case["b"]["size"], (name, a.size, case["a"]["size"])
+
+
+def time_yastn_sweep(yastn, work, passes, sync=None):
+    """Seconds per pass of yastn.tensordot over the sweep (1 untimed pass warms YASTN's meta caches, thread pools, pages)."""
+    for _, a, b, axes in work:
+        yastn.tensordot(a, b, axes=axes)
+    if sync:
+        sync()
+    t0 = time.perf_counter()
+    for _ in range(passes):
+        for _, a, b, axes in work:
+            yastn.tensordot(a, b, axes=axes)
+    if sync:
+        sync()
+    return (time.perf_counter() - t0) / passes
+
+
+def cpu_time_port(cases, cplx, reps):
+    """Fallback when baseline/_ref is absent: the oracle port of the numpy backend (kind "port")."""
     from oracle import backend_oracle as orc
     rng = np.random.default_rng(0)
-    flops, secs = 0, 0.0
+    secs = 0.0
     for name, case in cases:
         A = rng.uniform(-1, 1, case["a"]["size"]); B = rng.uniform(-1, 1, case["b"]["size"])
         if cplx:
             A = A + 1j * rng.uniform(-1, 1, A.size); B = B + 1j * rng.uniform(-1, 1, B.size)
-        orc.tensordot_f2m(A, B, case)   # warm (thread pools, page faults)
+        orc.tensordot_f2m(A, B, case)
         best = 1e30
         for _ in range(reps):
             t0 = time.perf_counter()
             orc.tensordot_f2m(A, B, case)
             best = min(best, time.perf_counter() - t0)
-        flops += case_flops(case["f2m"], cplx)
         secs += best
-    return flops, secs
+    return secs
 
 
-def cpu_baseline(cplx, sizes=(1024, 2048, 4096, 8192)):
-    cases = load_cases(sizes)
-    flops, secs = cpu_time_cases(cases, cplx, reps=2)
-    return {"value": flops / secs * 1e-9, "unit": "GFLOP/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": f"oracle/backend_oracle.py (numpy+OpenBLAS restatement of the reference numpy backend) on the D={list(sizes)} "
-                      f"P1+P2 subset of the sweep, best of 2 per contraction, {flops * 1e-9:.1f} GFLOP"}
+def cpu_reference_seconds(sizes, cplx, passes):
+    """(seconds per pass, kind, description) of the reference's CPU path on this box."""
+    cases = load_cases(tuple(sizes))
+    yastn = load_reference()
+    if yastn is None:
+        return cpu_time_port(cases, cplx, max(1, passes)), "port", "oracle/backend_oracle.py (numpy restatement; baseline/_ref not present)"
+    cfg = yastn.make_config(sym="U1", backend="np", tensordot_policy="fuse_to_matrix")
+    work = yastn_workload(yastn, cfg, sizes, cplx)
+    check_same_structure(work, cases)
+    return time_yastn_sweep(yastn, work, passes), "reference", "unmodified yastn (baseline/_ref) numpy backend, yastn.tensordot, OpenBLAS"
+
+
+def cpu_baseline(cplx, sizes):
+    cases = load_cases(tuple(sizes))
+    flops = sum(case_flops(c["f2m"], cplx) for _, c in cases)
+    secs, kind, what = cpu_reference_seconds(sizes, cplx, passes=1)
+    return {"value": flops / secs * 1e-9, "unit": "GFLOP/s", "cores": os.cpu_count(), "kind": kind,
+            "sample": f"{what}; one full pass of the sweep D={list(sizes)} x P1,P2,P3 after one warm-up pass, {flops * 1e-9:.1f} GFLOP in {secs:.2f} s"}
 
 
 def run_reference(args):
@@ -146,26 +229,73 @@ def run_reference(args):
     if rank != 0:
         return
     cplx = args.dtype == "c128"
-    sizes = tuple(s for s in args.sizes if s <= 8192) or (min(args.sizes),)
+    sizes = tuple(args.sizes)
     cases = load_cases(sizes)
-    for _ in range(max(args.warmup, 0) and 1):
-        cpu_time_cases(cases[:2], cplx, reps=1)
+    flops = sum(case_flops(c["f2m"], cplx) for _, c in cases)
     t0 = time.perf_counter()
-    flops_total, secs_total = 0, 0.0
-    for _ in range(args.steps):
-        f, s = cpu_time_cases(cases, cplx, reps=1)
-        flops_total += f
-        secs_total += s
-    val = flops_total / secs_total * 1e-9
+    yastn = load_reference()
+    if yastn is not None:
+        cfg = yastn.make_config(sym="U1", backend="np", tensordot_policy="fuse_to_matrix")
+        work = yastn_workload(yastn, cfg, sizes, cplx)
+        check_same_structure(work, cases)
+        secs = time_yastn_sweep(yastn, work, args.steps)
+        kind, what = "reference", "unmodified yastn (baseline/_ref), numpy backend, yastn.tensordot, OpenBLAS on all host cores"
+    else:
+        secs = cpu_time_port(cases, cplx, 1)
+        kind, what = "port", "oracle port of the reference numpy backend (baseline/_ref not present)"
+    val = flops / secs * 1e-9
+    cfg_line = workload_config(sizes, 1)
+    cfg_line["gflop_per_step"] = flops * 1e-9
     line = {"impl": "reference", "metric": "block-sparse tensordot GFLOP/s", "value": val, "unit": "GFLOP/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs_total / args.steps * 1e3, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": f"synthetic U(1) rank-4 tensordot sweep, D={list(sizes)} (bounded sample of D={list(args.sizes)}), P1+P2, fuse_to_matrix"},
-            "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": os.cpu_count(), "kind": "port",
-                             "sample": f"oracle port of the reference numpy backend, D={list(sizes)} P1+P2, {args.steps} passes"},
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic", "config": cfg_line,
+            "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": os.cpu_count(), "kind": kind,
+                             "sample": f"{what}; {args.steps} full passes of the sweep after one warm-up pass",
+                             "threads_env": os.environ.get("OMP_NUM_THREADS")},
             "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.perf_counter() - t0}
     print(json.dumps(line))
+
+
+def gpu_baseline(sizes, cplx, dev, flops):
+    """Same contractions through yastn.tensordot on the GPU: the reference's stock torch backend, and our backend module."""
+    import torch
+    yastn = load_reference()
+    if yastn is None:
+        return {"unavailable": "baseline/_ref not present"}
+    from yastn_b200 import yastn_backend
+    cases = load_cases(tuple(sizes))
+    out = {"unit": "GFLOP/s", "api": "yastn.tensordot, fuse_to_matrix, tensors resident on the GPU, wall clock around 3 passes with device sync"}
+    for key, backend in (("stock_torch", "torch"), ("ours", yastn_backend.module())):
+        cfg = yastn.make_config(sym="U1", backend=backend, default_device=str(dev), tensordot_policy="fuse_to_matrix")
+        work = yastn_workload(yastn, cfg, sizes, cplx)
+        check_same_structure(work, cases)
+        secs = time_yastn_sweep(yastn, work, 3, sync=lambda: torch.cuda.synchronize(dev))
+        out[key] = flops / secs * 1e-9
+        out[key + "_ms_per_step"] = secs * 1e3
+        del work
+        torch.cuda.empty_cache()
+    out["value"] = out["stock_torch"]
+    out["kind"] = "unmodified yastn (baseline/_ref) stock backend_torch on the same GPU"
+    return out
+
+
+def dmrg_sweep(which, timeout=900):
+    """One 2-site DMRG sweep, U(1)xU(1) Hubbard N=20 D=4096 complex128, in a fresh process (tools/dmrg_bench.py)."""
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "dmrg_bench.py"), "--model", "hubbard", "--N", "20", "--D", "4096", "--D0", "4096",
+           "--sweeps", "1", "--dtype", "complex128", "--backend", which] + (["--fused", "--gemm-roofline"] if which == "b200" else [])
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+        line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
+        d = json.loads(line)
+        if "sweep_s" not in d:
+            return d
+        out = {"sweep_s": d["sweep_s"][0], "energy": d["energy"][0]}
+        if d.get("gemm_roofline"):
+            out["gemm"] = d["gemm_roofline"]
+        return out
+    except Exception as e:   # a missing figure must not take the bench line down
+        return {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
 
 
 # -------------------------------------------------------------------------------------------------
@@ -181,6 +311,8 @@ def main():
     ap.add_argument("--dtype", default="f64", choices=["f64", "c128"])
     ap.add_argument("--sizes", type=int, nargs="+", default=list(DEFAULT_SIZES))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the stock-torch-backend-on-GPU leg")
+    ap.add_argument("--no-dmrg", action="store_true", help="skip the DMRG D=4096 sweep legs (about 2.5 minutes)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fuse", action="store_true", help="run unmerge as its own launch instead of the GEMM scatter epilogue")
     args = ap.parse_args()
@@ -231,6 +363,10 @@ def main():
 
     fuse = not args.no_fuse
 
+    def count_merge(data, m):
+        info = bk._merge_plans(data, m["order"], m["meta_new"], m["meta_mrg"], m["Dsize"])["fwd"].info()
+        launches[0] += (1 if info["items"] > 0 else 0) + (1 if info["tiled_records"] > 0 and info["records"] > info["tiled_records"] else 0)
+
     def contract(w, A, B, ev=None):
         """One fuse_to_matrix tensordot: merge A, merge B, grouped GEMM whose epilogue scatters into the unmerged
         block layout (3 launches; with --no-fuse the unmerge is a 4th launch, exactly the reference's call sequence)."""
@@ -240,9 +376,9 @@ def main():
         if ev is not None:
             ev[2].record()
         if ma is not None:
-            Am = bk.transpose_and_merge(A, ma["order"], ma["meta_new"], ma["meta_mrg"], ma["Dsize"]); launches[0] += 1
+            Am = bk.transpose_and_merge(A, ma["order"], ma["meta_new"], ma["meta_mrg"], ma["Dsize"]); count_merge(A, ma)
         if mb is not None:
-            Bm = bk.transpose_and_merge(B, mb["order"], mb["meta_new"], mb["meta_mrg"], mb["Dsize"]); launches[0] += 1
+            Bm = bk.transpose_and_merge(B, mb["order"], mb["meta_new"], mb["meta_mrg"], mb["Dsize"]); count_merge(B, mb)
         if ev is not None:
             ev[0].record()
         if fuse and st["unmerge"] is not None:
@@ -284,16 +420,24 @@ def main():
     ms = e0.elapsed_time(e1)
     n_launch = launches[0]
     clocks = sampler.stop() if rank == 0 else None
-    gemm_ms = sum(a.elapsed_time(b) for row in gemm_events for (a, b, _) in row)
+    # per-kernel shares from the events recorded inside the timed region.  P3 contractions run on the skinny (HBM-bound)
+    # kernel, P1 / P2 on the DMMA tile kernel: they are reported against different rooflines.
+    skinny = [w["name"].endswith("P3") for w in work]
+    gemm_ms = sum(a.elapsed_time(b) for row in gemm_events for (a, b, _), sk in zip(row, skinny) if not sk)
+    skinny_ms = sum(a.elapsed_time(b) for row in gemm_events for (a, b, _), sk in zip(row, skinny) if sk)
     merge_ms = sum(c.elapsed_time(a) for row in gemm_events for (a, _, c) in row)
     isz = 16 if cplx else 8
     merge_bytes = 0
-    for w in work:
+    skinny_bytes = 0
+    for w, sk in zip(work, skinny):
         for key in ("merge_a", "merge_b"):
             m = w["stage"][key]
             if m is not None:
                 merge_bytes += isz * (sum(x[1][1] - x[1][0] for x in m["meta_mrg"]) + m["Dsize"])
+        if sk:   # every element of the two merged operands is read once; the result is a few numbers
+            skinny_bytes += isz * sum(Da[0] * Da[1] + Db[0] * Db[1] for (_, _, _, Da, _, Db) in w["stage"]["dot"]["meta_dot"])
     own_flops = sum(w["flops"] for w in work)
+    tile_flops = sum(w["flops"] for w, sk in zip(work, skinny) if not sk)
 
     # end-to-end: host operands (pinned) -> H2D -> 4 backend calls -> D2H of the result
     e2e = None
@@ -384,19 +528,17 @@ def main():
             pass
         ms_step = ms / args.steps
         gflops = total_flops / (ms_step * 1e-3) * 1e-9
-        gemm_tflops = own_flops * args.steps / (gemm_ms * 1e-3) * 1e-12 if gemm_ms > 0 else 0.0
+        gemm_tflops = tile_flops * args.steps / (gemm_ms * 1e-3) * 1e-12 if gemm_ms > 0 else 0.0
+        cfg_line = workload_config(args.sizes, world)
+        cfg_line["gflop_per_step"] = total_flops * 1e-9
         line = {"metric": "block-sparse tensordot GFLOP/s", "value": gflops, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-                "config": {"workload": f"synthetic U(1) rank-4 block-sparse tensordot sweep (SURVEY 8d config 5): D={list(args.sizes)}, "
-                                       f"P1=A.F axes (3,0) and P2=A.B4 axes ((1,2,3),(2,1,0)), fuse_to_matrix pipeline merge/merge/GEMM+unmerge",
-                           "contractions_per_step": len(work), "gflop_per_step": total_flops * 1e-9,
-                           "l2": "inputs+outputs of the sweep (>10 GB) exceed L2; no flush needed",
-                           "sharding": "charge sectors FLOP-balanced over ranks, no collective" if world > 1 else "single GPU"},
+                "vs_baseline": None, "dtype": args.dtype, "data": "synthetic", "config": cfg_line,
                 "gpu_launches": n_launch,
-                "roofline": {"kernel": "yb::gemm_kernel (grouped DMMA.8x8x4 block GEMM)", "bound": "tensor", "achieved": gemm_tflops,
+                "roofline": {"kernel": "yb::gemm_kernel (grouped DMMA.8x8x4 block GEMM; P1 and P2 contractions)", "bound": "tensor", "achieved": gemm_tflops,
                              "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": gemm_tflops / FP64_PEAK_TFLOPS, "traffic": traffic, "traffic_of": traffic_of,
-                             "peak_source": "measured FP64 DMMA pipe peak, tools/microbench/fp64_pipes.cu (profiles/fp64_peaks_r01.json); cuBLAS DGEMM 8192^3 = 35.5",
+                             "peak_source": "measured FP64 DMMA pipe peak, tools/microbench/fp64_pipes.cu (profiles/fp64_peaks_r01.json); cuBLAS DGEMM 8192^3 = 35.5; "
+                                            "MEASURED_PEAKS.json has no FP64 figure",
                              "gemm_share_of_step": gemm_ms / ms if ms > 0 else None,
                              "epilogue": "fused unmerge scatter" if fuse else "plain store + separate unmerge launch"},
                 "roofline_merge": {"kernel": "yb::copy_kernel (transpose_and_merge of A and B)", "bound": "hbm",
@@ -405,11 +547,30 @@ def main():
                                    "frac": merge_bytes * args.steps / (merge_ms * 1e-3) * 1e-9 / HBM_PEAK_GBS if merge_ms > 0 else None,
                                    "share_of_step": merge_ms / ms if ms > 0 else None,
                                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if HBM_FROM_FILE else "fallback 6650 GB/s (B200_PROFILING.md)"},
+                "roofline_skinny": {"kernel": "yb::skinny_kernel (P3 contractions: K ~ 1e7, result blocks <= 4 x 4)", "bound": "hbm",
+                                    "achieved": skinny_bytes * args.steps / (skinny_ms * 1e-3) * 1e-9 if skinny_ms > 0 else None,
+                                    "peak": HBM_PEAK_GBS, "unit": "GB/s",
+                                    "frac": skinny_bytes * args.steps / (skinny_ms * 1e-3) * 1e-9 / HBM_PEAK_GBS if skinny_ms > 0 else None,
+                                    "share_of_step": skinny_ms / ms if ms > 0 else None},
                 "clocks": clocks}
         if e2e is not None:
             line["e2e"] = e2e
-        if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline(cplx)
+        if world == 1:
+            del work
+            torch.cuda.empty_cache()
+            if not args.no_cpu_baseline:
+                line["cpu_baseline"] = cpu_baseline(cplx, args.sizes)
+            if not args.no_gpu_baseline:
+                try:
+                    line["gpu_baseline"] = gpu_baseline(args.sizes, cplx, dev, total_flops)
+                except Exception as e:
+                    line["gpu_baseline"] = {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"}
+            if not args.no_dmrg:
+                torch.cuda.empty_cache()
+                ours, stock = dmrg_sweep("b200"), dmrg_sweep("torch")
+                line["dmrg_sweep_s"] = {"config": "U(1)xU(1) Hubbard chain N=20, 2-site DMRG, D=4096, complex128, one sweep from a random D=4096 MPS "
+                                                  "(BASELINE config 3 shape), unmodified yastn (baseline/_ref), fuse_to_matrix",
+                                        "ours": ours, "stock_torch_same_gpu": stock}
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()

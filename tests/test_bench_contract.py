@@ -22,9 +22,30 @@ def test_reference_arm_prints_one_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "block-sparse tensordot GFLOP/s" and d["unit"] == "GFLOP/s"
     assert d["higher_is_better"] is True and d["value"] > 0 and d["n_gpus"] == 1 and d["steps"] == 1
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    have_ref = os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "yastn"))
+    assert d["cpu_baseline"]["kind"] == ("reference" if have_ref else "port")     # the real yastn + numpy backend when installed
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert "P3" in d["config"]["workload"] and d["config"]["contractions_per_step"] == 3
     assert d["e2e"] == {"value": d["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_reference_arm_uses_all_host_threads_under_torchrun_env():
+    """torchrun exports OMP_NUM_THREADS=1 to its ranks; the reference arm must not inherit that (round-1 SCALE ratios were
+    inflated 3x by it)."""
+    r = _run(["--impl", "reference", "--steps", "1", "--warmup", "0", "--sizes", "1024", "--gpus", "2"],
+             env={"RANK": "0", "WORLD_SIZE": "2", "OMP_NUM_THREADS": "1"})
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([ln for ln in r.stdout.splitlines() if ln.strip()][0])
+    assert d["cpu_baseline"]["threads_env"] == str(os.cpu_count())
+
+
+def test_both_arms_describe_the_same_config():
+    sys.path.insert(0, ROOT)
+    import importlib
+    bench = importlib.import_module("bench")
+    a = bench.workload_config([1024, 16384], 1)
+    assert a == bench.workload_config((1024, 16384), 1) and "16384" in a["workload"]
 
 
 def test_reference_arm_other_ranks_stay_silent():

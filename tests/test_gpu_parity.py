@@ -153,8 +153,6 @@ def _run_f2m(bk, A, B, case):
 def test_tensordot_pipeline_vs_oracle(bk, name, dtype):
     """merge -> dot -> unmerge on benchmark-shaped structures (reference metas) against the CPU oracle."""
     case = bench_structs()[name]
-    if dtype == "complex128" and case["a"]["size"] > 3_000_000:
-        pytest.skip("oracle too slow")
     rng = np.random.default_rng(2)
     A = rng.uniform(-1, 1, case["a"]["size"]); B = rng.uniform(-1, 1, case["b"]["size"])
     if dtype == "complex128":
@@ -286,6 +284,46 @@ def test_fused_dot_unmerge_matches_two_calls(bk, name, dtype):
     bk.dot_unmerge(A1, B1, md, st["dot"]["Dsize"], um).backward(G)
     bk.unmerge(bk.dot(A2, B2, md, st["dot"]["Dsize"]), um).backward(G)
     assert torch.equal(A1.grad, A2.grad) and torch.equal(B1.grad, B2.grad)
+
+
+@pytest.mark.parametrize("name", ["U1_D8192_P1", "U1_D16384_P1", "U1_D16384_P2"])
+@pytest.mark.parametrize("dtype", ["float64", "complex128"])
+def test_fused_dot_unmerge_at_bench_sizes(bk, name, dtype):
+    """The launch bench.py times (grouped GEMM with the fused unmerge scatter, D = 8192 / 16384): bit-identical to
+    unmerge(dot(...)), and >= 8 sectors — the largest, the smallest, every kind of edge tile — equal to a float64 /
+    complex128 NUMPY product of the merged operands (host BLAS, not cuBLAS) to 1e-12."""
+    case = bench_structs()[name]
+    st = case["f2m"]
+    cplx = dtype == "complex128"
+    gen = torch.Generator(device="cuda").manual_seed(11)
+
+    def rnd(n):
+        x = torch.rand(n, dtype=torch.float64, device="cuda", generator=gen) * 2 - 1
+        return torch.complex(x, torch.rand(n, dtype=torch.float64, device="cuda", generator=gen) * 2 - 1) if cplx else x
+    A, B = rnd(case["a"]["size"]), rnd(case["b"]["size"])
+    ma, mb = st["merge_a"], st["merge_b"]
+    Am = A if ma is None else bk.transpose_and_merge(A, ma["order"], ma["meta_new"], ma["meta_mrg"], ma["Dsize"])
+    Bm = B if mb is None else bk.transpose_and_merge(B, mb["order"], mb["meta_new"], mb["meta_mrg"], mb["Dsize"])
+    md, Dsize = st["dot"]["meta_dot"], st["dot"]["Dsize"]
+    Cm = bk.dot(Am, Bm, md, Dsize)
+    if st["unmerge"] is not None:
+        two = bk.unmerge(Cm, st["unmerge"]["meta"])
+        one = bk.dot_unmerge(Am, Bm, md, Dsize, st["unmerge"]["meta"])
+        assert torch.equal(one, two)
+        del one, two
+    flops = [r[3][0] * r[3][1] * r[5][1] for r in md]
+    order = sorted(range(len(md)), key=lambda i: flops[i])
+    pick = {order[-1], order[-2], order[0], order[len(order) // 2]}
+    bn = 64 if cplx else 128
+    edge = {i for i in order if md[i][3][0] % 64 in range(1, 9) or md[i][5][1] % bn in range(1, 9)}    # a nearly empty last tile row / column
+    pick |= set(sorted(edge, key=lambda i: -flops[i])[:3])
+    pick |= set(order[:: max(1, len(order) // 5)])
+    assert len(pick) >= 8
+    for i in sorted(pick):
+        slc, Dc, sla, Da, slb, Db = md[i]
+        ref = Am[sla[0]:sla[1]].view(Da).cpu().numpy() @ Bm[slb[0]:slb[1]].view(Db).cpu().numpy()
+        got = Cm[slc[0]:slc[1]].view(Dc).cpu().numpy()
+        assert _relerr(got, ref) <= TOL, (name, dtype, i, Da, Db)
 
 
 def test_p3_runs_on_the_skinny_path_and_is_deterministic(bk):

@@ -84,6 +84,50 @@ def profiled(backend, device, prof):
     return mod
 
 
+def gemm_roofline(backend, cplx_hint):
+    """Copy of the backend module whose GEMM entry points (dot / dot_unmerge) are bracketed by CUDA events on the current
+    stream (no synchronisation inside the sweep) and whose algorithmic FLOPs are summed from meta_dot
+    (2*M*K*N per record, x4 for complex128).  ``report()`` returns TFLOP/s inside the kernel launches."""
+    import types
+    import torch
+    mod = types.ModuleType("roofline_" + backend.__name__)
+    for name in dir(backend):
+        if not name.startswith("__"):
+            setattr(mod, name, getattr(backend, name))
+    events, flops_of = [], {}
+
+    def flops(meta_dot, cplx):
+        key = id(meta_dot)
+        if key not in flops_of:
+            flops_of[key] = (meta_dot, sum(2 * Da[0] * Da[1] * Db[1] for (_, _, _, Da, _, Db) in meta_dot))
+        return flops_of[key][1] * (4 if cplx else 1)
+
+    def wrap(fn):
+        def f(Adata, Bdata, meta_dot, *rest):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn(Adata, Bdata, meta_dot, *rest)
+            e1.record()
+            events.append((e0, e1, flops(meta_dot, Adata.is_complex() or Bdata.is_complex())))
+            return out
+        return f
+    for name in ("dot", "dot_unmerge"):
+        if hasattr(backend, name):
+            setattr(mod, name, wrap(getattr(backend, name)))
+
+    def report():
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b, _ in events)
+        fl = sum(f for _, _, f in events)
+        big = [(a.elapsed_time(b), f) for a, b, f in events if f >= 1e9]
+        ms_big, fl_big = sum(x for x, _ in big), sum(f for _, f in big)
+        return {"calls": len(events), "gflop": fl * 1e-9, "gemm_s": ms * 1e-3, "tflops": fl / (ms * 1e-3) * 1e-12 if ms > 0 else None,
+                "frac_of_37.1": fl / (ms * 1e-3) * 1e-12 / 37.1 if ms > 0 else None,
+                "calls_over_1gflop": len(big), "tflops_over_1gflop": fl_big / (ms_big * 1e-3) * 1e-12 if ms_big > 0 else None,
+                "share_of_flops_over_1gflop": fl_big / fl if fl else None}
+    return mod, report
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--model", default="heisenberg")
@@ -100,6 +144,7 @@ def main():
     ap.add_argument("--fused", action="store_true", help="b200 only: fuse dot+unmerge into one launch (yastn_backend.enable_fused_tensordot)")
     ap.add_argument("--decomp-workers", type=int, default=None, help="b200 only: sector streams of svd/qr/eigh (1 = the reference's serial loop)")
     ap.add_argument("--profile", action="store_true", help="time every backend function (device-synchronised: perturbs the totals)")
+    ap.add_argument("--gemm-roofline", action="store_true", help="CUDA-event time and FLOP count of every dot / dot_unmerge launch (no sync inside the sweep)")
     args = ap.parse_args()
     from yastn_loader import load_yastn
     yastn = load_yastn(allow_reference_checkout=False)
@@ -125,6 +170,9 @@ def main():
         backend = args.backend
     device = "cpu" if args.backend == "np" else args.device
     prof = {}
+    roof = None
+    if args.gemm_roofline and device != "cpu" and not isinstance(backend, str):
+        backend, roof = gemm_roofline(backend, args.dtype == "complex128")
     if args.profile:
         backend = profiled(backend, device, prof)
     cfg_kw = dict(backend=backend, default_device=device, tensordot_policy=args.policy, default_dtype=args.dtype)
@@ -145,6 +193,8 @@ def main():
     line = {"model": args.model, "N": args.N, "D": args.D, "dtype": args.dtype, "backend": args.backend + ("+fused" if args.fused else ""), "device": device, "policy": args.policy,
             "sweep_s": times, "energy": energies, "bond_dims": max(psi.get_bond_dimensions()),
             "hot_calls": counts() if counts else None, "decomp_workers": args.decomp_workers}
+    if roof is not None:
+        line["gemm_roofline"] = roof()
     if args.profile:
         top = sorted(prof.items(), key=lambda kv: -kv[1][1])[:14]
         line["backend_profile"] = {k: {"calls": v[0], "s": round(v[1], 3)} for k, v in top}
