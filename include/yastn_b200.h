@@ -34,6 +34,10 @@ extern "C" {
 #define YB_F64 0
 #define YB_C128 1
 
+/* src_base of a copy record that has no source: the destination box is filled with zeros (cells of a merged block that no
+ * source block covers; replaces a memset of the whole destination) */
+#define YB_COPY_SRC_ZERO INT64_MIN
+
 /* yb_copy_run flags */
 #define YB_COPY_ZERO_DST 1 /* clear dst before scattering (merge with missing blocks)               */
 #define YB_COPY_CONJ 2     /* complex conjugate while copying (resolves torch's lazy conj bit)        */
@@ -56,8 +60,9 @@ const char* yb_last_error(void);
  * Records must write disjoint destinations.  itemsize is 8 (float64) or 16 (complex128).
  * ---------------------------------------------------------------------------------------------- */
 int yb_copy_plan_create(const int64_t* recs, int64_t nrec, int rank, int itemsize, int device, yb_copy_plan** out);
-/* info[0]=work items, [1]=elements moved, [2]=records kept after normalisation, [3]=records on the tiled-transpose path */
-int yb_copy_plan_info(const yb_copy_plan* plan, int64_t info[4]);
+/* info[0]=work items, [1]=elements moved (or zero-filled), [2]=records kept after normalisation, [3]=records on the
+ * tiled-transpose path, [4]=entries of the run table (rows of small records and zero-fill boxes) */
+int yb_copy_plan_info(const yb_copy_plan* plan, int64_t info[5]);
 int yb_copy_run(const yb_copy_plan* plan, const void* src, void* dst, int64_t dst_elems, int flags, void* stream);
 void yb_copy_plan_destroy(yb_copy_plan* plan);
 

@@ -31,7 +31,8 @@ class CpuCopyPlan:
         r = rank
         ext = self.recs[:, 2:2 + r]
         live = (ext > 0).all(axis=1)
-        self.src_n = int((self.recs[live, 0] + ((ext[live] - 1) * self.recs[live, 2 + r:2 + 2 * r]).sum(axis=1)).max() + 1) if live.any() else 0
+        src_live = live & (self.recs[:, 0] != np.iinfo(np.int64).min)
+        self.src_n = int((self.recs[src_live, 0] + ((ext[src_live] - 1) * self.recs[src_live, 2 + r:2 + 2 * r]).sum(axis=1)).max() + 1) if src_live.any() else 0
         self.dst_n = int((self.recs[live, 1] + ((ext[live] - 1) * self.recs[live, 2 + 2 * r:]).sum(axis=1)).max() + 1) if live.any() else 0
 
     def run(self, src_ptr, dst_ptr, dst_elems, flags, stream):

@@ -12,8 +12,11 @@ def exec_copy(recs, rank, src, dst):
         if np.prod(ext) == 0:
             continue
         idx = np.indices(tuple(int(e) for e in ext)).reshape(rank, -1)
-        so = sb + (idx * ss[:, None]).sum(axis=0)
         do = db + (idx * ds[:, None]).sum(axis=0)
+        if sb == np.iinfo(np.int64).min:      # YB_COPY_SRC_ZERO: zero-fill record
+            dst[do] = 0
+            continue
+        so = sb + (idx * ss[:, None]).sum(axis=0)
         dst[do] = src[so]
     return dst
 

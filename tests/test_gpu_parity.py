@@ -236,6 +236,36 @@ def test_full_size_linearity_and_roundtrip(bk, name):
         assert float(torch.linalg.norm(got - ref) / torch.linalg.norm(ref)) <= 1e-12
 
 
+@pytest.mark.parametrize("dtype", ["float64", "complex128"])
+def test_merge_zero_fills_only_the_holes(bk, dtype):
+    """Merged blocks with missing source blocks (1-, 2-, 3-d targets, ragged grids, single uncovered columns): the kernel
+    writes zeros into exactly the uncovered cells (zero-fill runs) — the destination is NOT memset — and every other element
+    of the output buffer, here pre-poisoned with NaN through the caching allocator, belongs to some record."""
+    rng = np.random.default_rng(0)
+    from yastn_b200 import plans as _plans
+    for g, Dn in ((1, (11,)), (2, (7, 9)), (3, (4, 5, 6)), (2, (5, 1)), (3, (3, 1, 4)), (2, (300, 170)), (2, (2000, 3))):
+        cuts = [sorted({0, d} | set(rng.integers(0, d + 1, 3).tolist())) for d in Dn]
+        cells = [tuple(c) for c in np.ndindex(*[len(c) - 1 for c in cuts])]
+        keep = [c for c in cells if rng.random() < 0.55] or cells[:1]
+        vol = int(np.prod(Dn))
+        meta_new = (((0,), Dn, (0, vol)),)
+        meta_mrg, lo = [], 0
+        for c in keep:
+            box = tuple((cuts[d][c[d]], cuts[d][c[d] + 1]) for d in range(g))
+            ext = tuple(b - a for a, b in box)
+            meta_mrg.append(((0,), (lo, lo + int(np.prod(ext))), ext, box, ext))
+            lo += int(np.prod(ext))
+        meta_mrg = tuple(meta_mrg)
+        x = rng.standard_normal(lo) + (1j * rng.standard_normal(lo) if dtype == "complex128" else 0)
+        ref = orc.transpose_and_merge(x, tuple(range(g)), meta_new, meta_mrg, vol)
+        recs, rank, covered = _plans.merge_records(tuple(range(g)), meta_new, meta_mrg)
+        assert covered == vol
+        poison = torch.full((vol,), float("nan"), dtype=torch.complex128 if dtype == "complex128" else torch.float64, device="cuda")
+        del poison                                     # the next allocation of this size gets the poisoned block back
+        out = bk.transpose_and_merge(_dev(x), tuple(range(g)), meta_new, meta_mrg, vol)
+        assert np.array_equal(out.cpu().numpy(), ref), (g, Dn)
+
+
 def test_rejects_cpu_and_unsupported_inputs(bk):
     case = bench_structs()["U1_D64_P1"]
     st = case["f2m"]["dot"]

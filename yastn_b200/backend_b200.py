@@ -93,9 +93,11 @@ def _merge_plans(data, order, meta_new, meta_mrg, Dsize):
     key = ("mrg", id(meta_mrg), tuple(order), Dsize, len(meta_new), data.dtype, data.device.index)
 
     def build():
+        # `covered` counts the zero-fill records of cells no source block covers: the destination needs no memset then
         recs, rank, covered = plans.merge_records(order, meta_new, meta_mrg)
         fwd = plans.CopyPlan(recs, rank, _ITEMSIZE[data.dtype], data.device.index, covered)
-        return {"fwd": fwd, "recs": recs, "rank": rank, "bwd": None}
+        src_read = int(recs[recs[:, 0] != plans.SRC_ZERO][:, 2:2 + rank].prod(axis=1).sum()) if recs.shape[0] else 0
+        return {"fwd": fwd, "recs": recs, "rank": rank, "bwd": None, "src_read": src_read}
     return _CACHE.get(key, meta_mrg, build)
 
 
@@ -159,7 +161,7 @@ class _TransposeAndMerge(torch.autograd.Function):
         ent = _merge_plans(grad, order, meta_new, meta_mrg, Dsize)
         plan = _bwd_copy_plan(ent, grad.dtype, grad.device.index)
         out = torch.empty(ctx.n_src, dtype=grad.dtype, device=grad.device)
-        _run_copy(plan, grad, out, zero=ent["fwd"].covered < ctx.n_src)
+        _run_copy(plan, grad, out, zero=ent["src_read"] < ctx.n_src)      # source blocks that took no part keep a zero gradient
         return out, None, None, None, None
 
 

@@ -141,6 +141,12 @@ int workspace_reserve(int device) {
 int stream_workspace(int device, cudaStream_t st, size_t ws_bytes, size_t nflags, void** ws, int** flags) {
     if (device < 0 || device >= 64) return fail(kErrArg, "yastn_b200: device index %d out of range", device);
     std::lock_guard<std::mutex> lk(ws_mu);
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) {
+        cudaGetLastError();
+        cap = cudaStreamCaptureStatusNone;
+    }
+    const bool capturing = cap != cudaStreamCaptureStatusNone;
     auto it = ws_table.find({device, st});
     if (it == ws_table.end()) {
         StreamWs e;
@@ -152,6 +158,11 @@ int stream_workspace(int device, cudaStream_t st, size_t ws_bytes, size_t nflags
             if (rc != kOk) return rc;
         }
         it = ws_table.emplace(std::make_pair(device, st), e).first;
+    }
+    // keep one spare around for the next unknown stream; allocation is only legal outside stream capture
+    if (!capturing && ws_spare[device].empty()) {
+        StreamWs s;
+        if (ws_alloc(device, kWsDefaultBytes, kWsDefaultFlags, &s) == kOk) ws_spare[device].push_back(s);
     }
     StreamWs& e = it->second;
     if (e.ws_bytes < ws_bytes || e.nflags < nflags) {

@@ -56,15 +56,39 @@ static_assert(sizeof(CopyRec) % 16 == 0 && sizeof(CopyRec) / 4 <= 64, "CopyRec i
 constexpr int kRecWords = sizeof(CopyRec) / 4;
 
 struct CopyItem {
-    int32_t rec_begin, rec_end;  // [rec_begin, rec_end) ; a single record unless this is a pack
+    int32_t rec_begin, rec_end;  // [rec_begin, rec_end) ; a single record unless this is a pack; kind 5: range of the run table
     uint32_t e0, ne;             // flat / rows: element range; tiled: slab range
-    int32_t kind;                // 0 flat, 1 pack, 2 tiled, 3 long rows, 4 short rows (3, 4: innermost dim contiguous on both sides)
+    int32_t kind;                // 0 flat, 1 pack, 2 tiled, 3 long rows, 4 short rows (3, 4: innermost dim contiguous on both sides),
+                                 // 5 batch of up to 32 contiguous runs
     int32_t pad_[3];
+};
+
+// A contiguous run of n elements (one row, or a piece of a row, of a small record): the whole description of the move, so a
+// warp fetches the metadata of 32 runs with ONE coalesced load.  Tensors made of thousands of sub-kilobyte blocks (U1xU1:
+// 2030 blocks, median 132 elements) were metadata-latency bound on the record path: item -> 192-byte record -> data is three
+// dependent DRAM round trips per kilobyte moved (ncu: 1.3 TB/s, 20 stall cycles per issue on the long scoreboard).
+struct alignas(16) CopyRun {
+    int64_t src, dst;
+    uint32_t n;
+    uint32_t flags;              // bit0: no source, store zeros (cells of a merged block that no source block covers)
+    uint32_t pad_[2];
+};
+static_assert(sizeof(CopyRun) == 32, "CopyRun is fetched as two 16-byte words per lane");
+constexpr int kRunBatch = 32;              // runs per batch item (one per lane)
+constexpr int64_t kRunRecMax = 1 << 15;    // records up to this many elements go to the run table ...
+constexpr int64_t kRunRowMin = 8;          // ... if their rows have at least this many elements
+constexpr int64_t kRunPiece = 4096;        // longest run (longer rows are cut)
+
+struct RunSmem {                           // per warp
+    int64_t src[kRunBatch], dst[kRunBatch];
+    uint32_t start[kRunBatch + 1];
+    uint32_t flags[kRunBatch];
 };
 
 constexpr int kHostDims = 24;   // rank limit of an input record (YASTN tensors have at most ~12 legs)
 struct HostRec {                 // fixed arrays: plan construction handles thousands of records, no per-record heap traffic
     int64_t src_base, dst_base;
+    bool zero;                   // no source: fill the destination box with zeros
     int nd;
     int64_t ext[kHostDims], sstr[kHostDims], dstr[kHostDims];
 };
@@ -408,19 +432,95 @@ __device__ __noinline__ void item_pack(const CopyRec* __restrict__ recs, int rec
     }
 }
 
+// batch of up to 32 contiguous runs: lane j fetches run j (one coalesced 1 KB load for the warp), an inclusive scan of the
+// lengths lays the runs on one line of `total` elements, and the warp walks that line 32 elements per load instruction —
+// every lane keeps a cursor (run index) that only moves forward, so runs of any length keep all lanes and 64 bytes of loads
+// per lane busy.  Addresses of a trip are resolved first (branches, shared memory), then all loads issue back to back.
+template <typename T, bool CONJ>
+__device__ __noinline__ void item_runs(const CopyRun* __restrict__ runs, int begin, int end, RunSmem& sm, const T* __restrict__ src,
+                                       T* __restrict__ dst, int lane) {
+    constexpr int kUnroll = 64 / sizeof(T);
+    const int nrun = end - begin;
+    int64_t rs = 0, rd = 0;
+    uint32_t rn = 0, rf = 0;
+    if (lane < nrun) {
+        const uint4* g = reinterpret_cast<const uint4*>(runs + begin + lane);
+        const uint4 w0 = g[0], w1 = g[1];
+        rs = (int64_t)(((uint64_t)w0.y << 32) | w0.x);
+        rd = (int64_t)(((uint64_t)w0.w << 32) | w0.z);
+        rn = w1.x;
+        rf = w1.y;
+    }
+    uint32_t e = rn;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, e, d);
+        if (lane >= d) e += t;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, e, 31);
+    __syncwarp();      // the previous item of this warp is done with sm
+    sm.src[lane] = rs;
+    sm.dst[lane] = rd;
+    sm.flags[lane] = rf;
+    sm.start[lane] = e - rn;
+    if (lane == 31) sm.start[kRunBatch] = total;
+    __syncwarp();
+    int j = 0;
+    uint32_t cstart = 0, cend = sm.start[1];
+    int64_t csrc = sm.src[0], cdst = sm.dst[0];
+    bool czero = sm.flags[0] & 1;
+    for (uint32_t base = 0; base < total; base += 32 * kUnroll) {
+        int64_t so[kUnroll], dof[kUnroll];
+        uint32_t live = 0, fill = 0;
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const uint32_t p = base + 32 * u + lane;
+            so[u] = 0;
+            dof[u] = 0;
+            if (p < total) {
+                if (p >= cend) {
+                    do {
+                        ++j;
+                        cend = sm.start[j + 1];
+                    } while (p >= cend);
+                    cstart = sm.start[j];
+                    csrc = sm.src[j];
+                    cdst = sm.dst[j];
+                    czero = sm.flags[j] & 1;
+                }
+                so[u] = csrc + (p - cstart);
+                dof[u] = cdst + (p - cstart);
+                live |= 1u << u;
+                if (czero) fill |= 1u << u;
+            }
+        }
+        T v[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) v[u] = load_if<T, CONJ>(((live & ~fill) >> u) & 1, src + so[u]);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+            if ((live >> u) & 1) dst[dof[u]] = v[u];
+    }
+}
+
 // One warp = one work item at a time; warps never synchronise with each other, so an SM keeps 32 independent
 // item -> record -> loads -> stores chains in flight (a CTA-wide item pipeline kept 3 and starved on tensors made of
 // thousands of small blocks).  Transposing slabs are a separate launch (tiled_kernel).
 template <typename T, bool CONJ>
 __global__ void __launch_bounds__(kCopyThreads, 4)
-copy_kernel(const CopyRec* __restrict__ recs, const CopyItem* __restrict__ items, int nitems,
+copy_kernel(const CopyRec* __restrict__ recs, const CopyItem* __restrict__ items, int nitems, const CopyRun* __restrict__ runs,
             const T* __restrict__ src, T* __restrict__ dst) {
     __shared__ CopyRec srecs[kCopyWarps];
+    __shared__ RunSmem sruns[kCopyWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     CopyRec& srec = srecs[warp];
     const int nwarps = gridDim.x * kCopyWarps;
     for (int it = blockIdx.x * kCopyWarps + warp; it < nitems; it += nwarps) {
         const CopyItem item = items[it];
+        if (item.kind == 5) {
+            item_runs<T, CONJ>(runs, item.rec_begin, item.rec_end, sruns[warp], src, dst, lane);
+            continue;
+        }
         if (item.kind == 1) {
             item_pack<T, CONJ>(recs, item.rec_begin, item.rec_end, srec, src, dst, lane);
             continue;
@@ -453,7 +553,8 @@ struct yb_copy_plan {
     int itemsize = 0, device = 0;
     int nitems = 0, nwarp_items = 0;
     int64_t elems = 0, nrecs = 0, ntiled = 0;
-    DeviceTable recs, items;
+    DeviceTable recs, items, runs;
+    int64_t nruns = 0;
     int grid = 0, grid_tiled = 0;
 };
 
@@ -583,21 +684,46 @@ extern "C" int yb_copy_plan_create(const int64_t* recs, int64_t nrec, int rank, 
 
     std::vector<HostRec> host;
     host.reserve((size_t)nrec);
+    std::vector<CopyRun> runs;
+    int64_t zero_elems = 0;
     const int64_t w = 2 + 3 * (int64_t)rank;
     for (int64_t i = 0; i < nrec; ++i) {
         const int64_t* p = recs + i * w;
         HostRec r;
         r.src_base = p[0];
         r.dst_base = p[1];
+        r.zero = p[0] == YB_COPY_SRC_ZERO;
         r.nd = rank;
         for (int k = 0; k < rank; ++k) {
             r.ext[k] = p[2 + k];
             r.sstr[k] = p[2 + rank + k];
             r.dstr[k] = p[2 + 2 * rank + k];
         }
+        if (r.zero) {   // no source: give the box the strides of its destination so that contiguous dims merge
+            r.src_base = 0;
+            for (int k = 0; k < rank; ++k) r.sstr[k] = r.dstr[k];
+        }
         for (int k = 0; k < rank; ++k)
             if (r.ext[k] < 0 || r.sstr[k] < 0 || r.dstr[k] < 0) return fail(kErrArg, "yb_copy_plan_create: negative extent/stride in record %lld", (long long)i);
         if (!normalise(r)) continue;
+        if (r.zero) {   // straight to the run table: one run per contiguous row (piece) of the box
+            const bool inner = r.dstr[r.nd - 1] == 1;
+            const int outer = inner ? r.nd - 1 : r.nd;
+            const int64_t L = inner ? r.ext[r.nd - 1] : 1;
+            int64_t idx[kHostDims] = {0}, rows = 1;
+            for (int k = 0; k < outer; ++k) rows *= r.ext[k];
+            for (int64_t q = 0; q < rows; ++q) {
+                int64_t dof = r.dst_base;
+                for (int k = 0; k < outer; ++k) dof += idx[k] * r.dstr[k];
+                for (int64_t c = 0; c < L; c += kRunPiece) {
+                    CopyRun run = {0, dof + c, (uint32_t)std::min<int64_t>(kRunPiece, L - c), 1u, {0, 0}};
+                    runs.push_back(run);
+                }
+                for (int k = outer - 1; k >= 0 && ++idx[k] == r.ext[k]; --k) idx[k] = 0;
+            }
+            zero_elems += rows * L;
+            continue;
+        }
         split_to_limits(r, host);
     }
 
@@ -612,14 +738,55 @@ extern "C" int yb_copy_plan_create(const int64_t* recs, int64_t nrec, int rank, 
     const uint32_t item_elems = item_size(all_elems, sms, itemsize);
     std::vector<CopyRec> drecs;
     std::vector<CopyItem> items, cta_items;
-    int64_t elems = 0, ntiled = 0, nslabs = 0;
+    std::vector<char> on_runs(host.size(), 0);
+    int64_t elems = zero_elems, ntiled = 0, nslabs = 0;
     drecs.reserve(host.size());
+    // Records that are a few contiguous rows go to the run table (see CopyRun): everything the kernel needs to move a run
+    // is in its 32-byte entry.  Zero-fill boxes always do (they have no record path).
+    for (size_t i = 0; i < host.size(); ++i) {
+        const HostRec& h = host[i];
+        const int last = h.nd - 1;
+        if (h.nd > 2 || h.sstr[last] != 1 || h.dstr[last] != 1) continue;
+        const int64_t L = h.ext[last], rows = h.nd == 2 ? h.ext[0] : 1;
+        if (L * rows > kRunRecMax || (h.nd == 2 && L < kRunRowMin)) continue;
+        on_runs[i] = 1;
+        for (int64_t r = 0; r < rows; ++r) {
+            const int64_t so = h.src_base + (h.nd == 2 ? r * h.sstr[0] : 0), dof = h.dst_base + (h.nd == 2 ? r * h.dstr[0] : 0);
+            for (int64_t c = 0; c < L; c += kRunPiece) {
+                CopyRun run;
+                run.src = so + c;
+                run.dst = dof + c;
+                run.n = (uint32_t)std::min<int64_t>(kRunPiece, L - c);
+                run.flags = 0u;
+                run.pad_[0] = run.pad_[1] = 0;
+                runs.push_back(run);
+            }
+        }
+        elems += L * rows;
+    }
+    {   // batches: up to 32 runs and about item_elems elements each
+        size_t b = 0;
+        while (b < runs.size()) {
+            size_t e = b;
+            uint64_t acc = 0;
+            while (e < runs.size() && e - b < (size_t)kRunBatch && (acc == 0 || acc + runs[e].n <= std::max<uint32_t>(item_elems, 1024))) acc += runs[e++].n;
+            CopyItem it = {(int32_t)b, (int32_t)e, 0, 0, 5, {0, 0, 0}};
+            items.push_back(it);
+            b = e;
+        }
+    }
     // large records first in table order; tiny ones are packed afterwards
     std::vector<int> small_idx;
     for (size_t i = 0; i < host.size(); ++i) {
         const HostRec& h = host[i];
         CopyRec c;
         memset(&c, 0, sizeof(c));
+        if (on_runs[i]) {          // keeps the record indices aligned with `host`; never referenced by an item
+            c.nd = 1;
+            c.tile_a = c.tile_b = -1;
+            drecs.push_back(c);
+            continue;
+        }
         c.src_base = h.src_base;
         c.dst_base = h.dst_base;
         c.nd = h.nd;
@@ -660,6 +827,7 @@ extern "C" int yb_copy_plan_create(const int64_t* recs, int64_t nrec, int rank, 
     const uint32_t per_item = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(4, nslabs / (2ll * sms * 4)));
     for (size_t i = 0; i < drecs.size(); ++i) {
         const CopyRec& c = drecs[i];
+        if (on_runs[i]) continue;
         if (c.tile_a >= 0) {
             const uint64_t nslab = (uint64_t)c.tiles_a * c.tiles_b * c.outer_total;
             for (uint64_t s0 = 0; s0 < nslab; s0 += per_item) {
@@ -709,12 +877,14 @@ extern "C" int yb_copy_plan_create(const int64_t* recs, int64_t nrec, int rank, 
     plan->elems = elems;
     plan->nrecs = (int64_t)host.size();
     plan->ntiled = ntiled;
+    plan->nruns = (int64_t)runs.size();
     int prev = 0;
     cudaGetDevice(&prev);
     int rc = kOk;
     if (cudaSetDevice(device) != cudaSuccess) rc = fail(kErrCuda, "yb_copy_plan_create: cudaSetDevice(%d) failed", device);
     if (rc == kOk) rc = plan->recs.upload(drecs.data(), drecs.size() * sizeof(CopyRec));
     if (rc == kOk) rc = plan->items.upload(items.data(), items.size() * sizeof(CopyItem));
+    if (rc == kOk) rc = plan->runs.upload(runs.data(), runs.size() * sizeof(CopyRun));
     if (rc == kOk) {
         plan->grid = std::min((nwarp_items + kCopyWarps - 1) / kCopyWarps, sms * 4);
         plan->grid_tiled = std::min((int)cta_items.size(), sms * 4);
@@ -723,6 +893,7 @@ extern "C" int yb_copy_plan_create(const int64_t* recs, int64_t nrec, int rank, 
     if (rc != kOk) {
         plan->recs.release();
         plan->items.release();
+        plan->runs.release();
         delete plan;
         return rc;
     }
@@ -730,12 +901,13 @@ extern "C" int yb_copy_plan_create(const int64_t* recs, int64_t nrec, int rank, 
     return kOk;
 }
 
-extern "C" int yb_copy_plan_info(const yb_copy_plan* plan, int64_t info[4]) {
+extern "C" int yb_copy_plan_info(const yb_copy_plan* plan, int64_t info[5]) {
     if (!plan || !info) return fail(kErrArg, "yb_copy_plan_info: null argument");
     info[0] = plan->nitems;
     info[1] = plan->elems;
     info[2] = plan->nrecs;
     info[3] = plan->ntiled;
+    info[4] = plan->nruns;
     return kOk;
 }
 
@@ -744,7 +916,7 @@ template <typename T, bool CONJ>
 int launch_copy(const yb_copy_plan* plan, const CopyRec* recs, const CopyItem* items, const CopyItem* titems, int ntiled_items,
                 const T* src, T* dst, cudaStream_t st) {
     if (plan->nwarp_items > 0)
-        copy_kernel<T, CONJ><<<plan->grid, kCopyThreads, 0, st>>>(recs, items, plan->nwarp_items, src, dst);
+        copy_kernel<T, CONJ><<<plan->grid, kCopyThreads, 0, st>>>(recs, items, plan->nwarp_items, (const CopyRun*)plan->runs.ptr, src, dst);
     if (ntiled_items > 0) {
         tiled_kernel<T, CONJ><<<plan->grid_tiled, kCopyThreads, 0, st>>>(recs, titems, ntiled_items, src, dst);
     }
@@ -783,5 +955,6 @@ extern "C" void yb_copy_plan_destroy(yb_copy_plan* plan) {
     if (!plan) return;
     plan->recs.release();
     plan->items.release();
+    plan->runs.release();
     delete plan;
 }

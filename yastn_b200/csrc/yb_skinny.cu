@@ -86,41 +86,65 @@ __device__ __forceinline__ double2 sk_ldcg(const double2* p) { return __ldcg(p);
 __device__ __forceinline__ void sk_stcg(double* p, double v) { __stcg(p, v); }
 __device__ __forceinline__ void sk_stcg(double2* p, double2 v) { __stcg(p, v); }
 
-// Loads the NT elements (x = 0..NT) of one operand at contraction index c; elements beyond `ext` are zero.
-//   sx == 1 (a row of `ext` contiguous elements per contraction index): 16-byte loads when `vec` (float64, aligned rows)
-template <typename T, int NT>
-__device__ __forceinline__ void sk_load(const T* __restrict__ base, int64_t sx, int64_t sc, int64_t c, int ext, bool vec, bool ok,
-                                        bool conj, T* out) {
+// Loads the NT elements (x = 0..NT) of one operand at contraction index c; elements beyond `ext`, and everything when !ok,
+// are zero.  Branch-free on purpose: out-of-range indices are CLAMPED to a valid element and the value is discarded by a
+// select, so all loads of a trip are issued back to back (with guarded loads the compiler emitted one branch region per
+// load and the warp waited for each in turn: ncu showed 38 stall cycles per issue on the long scoreboard, 15 % of HBM).
+//   full (sx == 1, ext == NT, float64, rows 16-byte aligned): a row of NT contiguous elements per contraction index is
+//   read with 16-byte loads.
+template <typename T, int NT, bool FULL>
+__device__ __forceinline__ void sk_load(const T* __restrict__ base, int64_t sx, int64_t sc, int64_t c, int ext, bool ok, bool conj, T* out) {
     const T* row = base + c * sc;
+    if constexpr (FULL) {
+        static_assert(sizeof(T) == 8 && NT >= 2, "16-byte row loads are a float64 path");
 #pragma unroll
-    for (int x = 0; x < NT; ++x) out[x] = sk_zero(T{});
-    if (!ok) return;
-    if constexpr (sizeof(T) == 8 && NT >= 2) {
-        if (vec) {
+        for (int x = 0; x < NT; x += 2) {
+            const double2 v = *reinterpret_cast<const double2*>(row + x);
+            out[x] = ok ? v.x : 0.0;
+            out[x + 1] = ok ? v.y : 0.0;
+        }
+    } else {
 #pragma unroll
-            for (int x = 0; x < NT; x += 2) {
-                if (x + 1 < ext) {
-                    const double2 v = *reinterpret_cast<const double2*>(row + x);
-                    out[x] = v.x;
-                    out[x + 1] = v.y;
-                } else if (x < ext) {
-                    out[x] = row[x];
-                }
-            }
-            return;
+        for (int x = 0; x < NT; ++x) {
+            const int xs = x < ext ? x : ext - 1;
+            const T v = sk_conj(row[xs * sx], conj);
+            out[x] = (ok && x < ext) ? v : sk_zero(T{});
         }
     }
+}
+
+// The trips of one part.  VA / VB (16-byte row loads of A / B) are template parameters so that the loop body is one basic
+// block: every lane runs the same number of trips (lanes past the end work on a clamped index and discard the value).
+template <bool CPLX, int XT, int YT, bool VA, bool VB>
+__device__ __forceinline__ void sk_accumulate(typename SkT<CPLX>::T (&acc)[XT][YT], const typename SkT<CPLX>::T* __restrict__ pa,
+                                              const typename SkT<CPLX>::T* __restrict__ pb, const GemmSegment& S, int M, int N,
+                                              int64_t c_begin, int64_t c_end, int lane, bool conjA, bool conjB) {
+    using T = typename SkT<CPLX>::T;
+    constexpr int U0 = (CPLX ? 8 : 16) / (XT + YT);          // >= 128 bytes of loads in flight per lane
+    constexpr int U = U0 < 1 ? 1 : (U0 > 8 ? 8 : U0);
+    const int64_t clast = c_end - 1;
+    for (int64_t c0 = c_begin; c0 < c_end; c0 += 32 * U) {
+        T a[U][XT], b[U][YT];
 #pragma unroll
-    for (int x = 0; x < NT; ++x)
-        if (x < ext) out[x] = sk_conj(row[x * sx], conj);
+        for (int u = 0; u < U; ++u) {
+            const int64_t cc = c0 + lane + 32 * u;
+            const bool ok = cc <= clast;
+            const int64_t cs = ok ? cc : clast;
+            sk_load<T, XT, VA>(pa, S.sAm, S.sAk, cs, M, ok, conjA, a[u]);
+            sk_load<T, YT, VB>(pb, S.sBn, S.sBk, cs, N, ok, conjB, b[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int x = 0; x < XT; ++x)
+#pragma unroll
+                for (int y = 0; y < YT; ++y) sk_fma(acc[x][y], a[u][x], b[u][y]);
+    }
 }
 
 template <bool CPLX, int XT, int YT>
 __global__ void __launch_bounds__(kSkThreads) skinny_kernel(const SkArgs g) {
     using T = typename SkT<CPLX>::T;
-    constexpr int LOADS = XT + YT;
-    constexpr int U0 = (CPLX ? 8 : 16) / LOADS;          // >= 128 bytes of loads in flight per lane
-    constexpr int U = U0 < 1 ? 1 : (U0 > 8 ? 8 : U0);
     constexpr int NE = XT * YT;
     const int lane = threadIdx.x & 31;
     const int w = blockIdx.x * kSkWarps + (threadIdx.x >> 5);
@@ -146,24 +170,17 @@ __global__ void __launch_bounds__(kSkThreads) skinny_kernel(const SkArgs g) {
             const GemmSegment S = g.segs[part.seg];
             const T* pa = A + S.offA;
             const T* pb = B + S.offB;
-            const bool vecA = !CPLX && S.sAm == 1 && ((reinterpret_cast<uintptr_t>(pa) & 15) == 0) && ((S.sAk & 1) == 0);
-            const bool vecB = !CPLX && S.sBn == 1 && ((reinterpret_cast<uintptr_t>(pb) & 15) == 0) && ((S.sBk & 1) == 0);
-            for (int64_t c = (int64_t)part.c0 + lane; c < part.c1; c += 32 * U) {
-                T a[U][XT], b[U][YT];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int64_t cc = c + 32 * u;
-                    const bool ok = cc < part.c1;
-                    sk_load<T, XT>(pa, S.sAm, S.sAk, cc, P.M, vecA, ok, conjA, a[u]);
-                    sk_load<T, YT>(pb, S.sBn, S.sBk, cc, P.N, vecB, ok, conjB, b[u]);
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u)
-#pragma unroll
-                    for (int x = 0; x < XT; ++x)
-#pragma unroll
-                        for (int y = 0; y < YT; ++y) sk_fma(acc[x][y], a[u][x], b[u][y]);
-            }
+            const bool vecA = !CPLX && XT >= 2 && P.M == XT && S.sAm == 1 && ((reinterpret_cast<uintptr_t>(pa) & 15) == 0) && ((S.sAk & 1) == 0);
+            const bool vecB = !CPLX && YT >= 2 && P.N == YT && S.sBn == 1 && ((reinterpret_cast<uintptr_t>(pb) & 15) == 0) && ((S.sBk & 1) == 0);
+            constexpr bool CANA = !CPLX && XT >= 2, CANB = !CPLX && YT >= 2;
+            if (CANA && CANB && vecA && vecB)
+                sk_accumulate<CPLX, XT, YT, CANA, CANB>(acc, pa, pb, S, P.M, P.N, part.c0, part.c1, lane, conjA, conjB);
+            else if (CANA && vecA)
+                sk_accumulate<CPLX, XT, YT, CANA, false>(acc, pa, pb, S, P.M, P.N, part.c0, part.c1, lane, conjA, conjB);
+            else if (CANB && vecB)
+                sk_accumulate<CPLX, XT, YT, false, CANB>(acc, pa, pb, S, P.M, P.N, part.c0, part.c1, lane, conjA, conjB);
+            else
+                sk_accumulate<CPLX, XT, YT, false, false>(acc, pa, pb, S, P.M, P.N, part.c0, part.c1, lane, conjA, conjB);
         }
         if (!(part.flags & 2)) continue;
 
@@ -254,6 +271,47 @@ int launch_y(int yt, int grid, const SkArgs& a, cudaStream_t st) {
     }
 }
 
+template <bool CPLX, int XT, int YT>
+int occupancy_xy(int* occ) {
+    if constexpr (XT * YT > skinny_entries(CPLX)) {
+        *occ = 0;
+        return kOk;
+    } else {
+        YB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, skinny_kernel<CPLX, XT, YT>, kSkThreads, 0));
+        return kOk;
+    }
+}
+
+template <bool CPLX, int XT>
+int occupancy_y(int yt, int* occ) {
+    switch (yt) {
+        case 1: return occupancy_xy<CPLX, XT, 1>(occ);
+        case 2: return occupancy_xy<CPLX, XT, 2>(occ);
+        case 4: return occupancy_xy<CPLX, XT, 4>(occ);
+        default: return occupancy_xy<CPLX, XT, 8>(occ);
+    }
+}
+
+template <bool CPLX>
+int occupancy_x(int xt, int yt, int* occ) {
+    static int cache[2][4][4] = {};   // [cplx][log2 xt][log2 yt]; the answer depends on the kernel only
+    auto lg = [](int v) { return v == 1 ? 0 : (v == 2 ? 1 : (v == 4 ? 2 : 3)); };
+    int& c = cache[CPLX ? 1 : 0][lg(xt)][lg(yt)];
+    if (c > 0) {
+        *occ = c;
+        return kOk;
+    }
+    int rc;
+    switch (xt) {
+        case 1: rc = occupancy_y<CPLX, 1>(yt, occ); break;
+        case 2: rc = occupancy_y<CPLX, 2>(yt, occ); break;
+        case 4: rc = occupancy_y<CPLX, 4>(yt, occ); break;
+        default: rc = occupancy_y<CPLX, 8>(yt, occ); break;
+    }
+    if (rc == kOk) c = *occ;
+    return rc;
+}
+
 template <bool CPLX>
 int launch_x(int xt, int yt, int grid, const SkArgs& a, cudaStream_t st) {
     switch (xt) {
@@ -286,7 +344,12 @@ int skinny_create(const std::vector<GemmProblem>& hp, const std::vector<GemmSegm
     plan->yt = pow2ceil(maxN);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    const int64_t max_warps = (int64_t)sms * kSkWarps * 4;
+    // one share per RESIDENT warp: the kernels use 64..250 registers, i.e. 1..4 CTAs per SM (a grid of 4 CTAs per SM on a
+    // kernel that fits 2 ran as 2.05 waves in the first version)
+    int occ = 0;
+    int rc0 = cplx ? occupancy_x<true>(plan->xt, plan->yt, &occ) : occupancy_x<false>(plan->xt, plan->yt, &occ);
+    if (rc0 != kOk || occ < 1) occ = 1;
+    const int64_t max_warps = (int64_t)sms * kSkWarps * occ;
     const int64_t chunk = std::max<int64_t>(kSkMinChunk, (W + max_warps - 1) / max_warps);
 
     std::vector<SkPart> parts;

@@ -53,8 +53,65 @@ def _pack(src_base, dst_base, ext, sstr, dstr):
     return np.ascontiguousarray(recs), r
 
 
-def merge_records(order, meta_new, meta_mrg):
-    """Copy records of transpose_and_merge. Returns (recs, rank, covered_elements)."""
+SRC_ZERO = np.iinfo(np.int64).min      # YB_COPY_SRC_ZERO: a record without source, its destination box is filled with zeros
+_ZERO_ROWS_MAX = 1 << 16               # above this many zero rows a memset of the whole destination is cheaper than the table
+
+
+def _zero_records(grp, lo, hi, Dn_new, sln_new, rank):
+    """Boxes of the merged blocks that no source block covers, as zero-fill records (src_base = SRC_ZERO).
+
+    The reference allocates the merged tensor with zeros and scatters the source blocks into it
+    (yastn/backend/_backend_torch_backwards.py:349-363); charge sectors that are absent from the tensor leave holes (20-30 % of
+    the merges of a CTMRG / Hubbard run).  The source rectangles of one merged block lie on a grid (row segments x
+    column segments; one segment list per fused leg in the N-d case): the holes are the grid cells no record occupies.
+    Returns (records [m, 2 + 3 * rank] or None when a plain memset is the better plan, number of zero elements)."""
+    g = lo.shape[1]
+    vol = np.bincount(grp, weights=(hi - lo).prod(axis=1).astype(np.float64), minlength=Dn_new.shape[0])
+    holes = np.nonzero(vol < Dn_new.prod(axis=1))[0]
+    if holes.size == 0:
+        return np.zeros((0, 2 + 3 * rank), dtype=I64), 0
+    if g > rank:
+        return None, 0
+    order = np.argsort(grp, kind="stable")
+    bounds = np.searchsorted(grp[order], np.arange(Dn_new.shape[0] + 1))
+    out, rows, zeros = [], 0, 0
+    for t in holes:
+        idx = order[bounds[t]:bounds[t + 1]]
+        Dn = Dn_new[t]
+        cuts = [np.unique(np.concatenate(([0, Dn[d]], lo[idx, d], hi[idx, d]))) for d in range(g)]
+        occ = np.zeros([c.size - 1 for c in cuts], dtype=bool)
+        for i in idx:
+            occ[tuple(slice(np.searchsorted(cuts[d], lo[i, d]), np.searchsorted(cuts[d], hi[i, d])) for d in range(g))] = True
+        nstr = _cstrides(Dn[None, :])[0]
+        free = np.argwhere(~occ)
+        k = 0
+        while k < free.shape[0]:                        # argwhere is row-major: neighbours along the last dim are consecutive
+            c0 = free[k]
+            e = k + 1
+            while e < free.shape[0] and (free[e, :-1] == c0[:-1]).all() and free[e, -1] == free[e - 1, -1] + 1:
+                e += 1
+            b_lo = np.array([cuts[d][c0[d]] for d in range(g)], dtype=I64)
+            b_hi = np.array([cuts[d][c0[d] + 1] for d in range(g)], dtype=I64)
+            b_hi[-1] = cuts[-1][free[e - 1, -1] + 1]
+            ext = b_hi - b_lo
+            rec = np.zeros(2 + 3 * rank, dtype=I64)
+            rec[0], rec[1] = SRC_ZERO, sln_new[t] + (b_lo * nstr).sum()
+            rec[2:2 + rank] = 1
+            rec[2:2 + g] = ext
+            rec[2 + 2 * rank:2 + 2 * rank + g] = nstr
+            out.append(rec)
+            rows += int(ext[:-1].prod()) if g > 1 else 1
+            zeros += int(ext.prod())
+            k = e
+    if rows > _ZERO_ROWS_MAX or zeros != int((Dn_new[holes].prod(axis=1) - vol[holes]).sum()):
+        return None, 0                                   # too fragmented (or overlapping source boxes): memset instead
+    return np.array(out, dtype=I64).reshape(len(out), 2 + 3 * rank), zeros
+
+
+def merge_records(order, meta_new, meta_mrg, zero_records=True):
+    """Copy records of transpose_and_merge.  Returns (recs, rank, covered): ``covered`` = destination elements the records
+    write, including the zero-fill records of uncovered cells (``zero_records``); a caller whose ``covered`` is below
+    ``Dsize`` must clear the destination first."""
     n = len(meta_mrg)
     r = len(order)
     if n == 0:
@@ -101,7 +158,14 @@ def merge_records(order, meta_new, meta_mrg):
         raise ValueError("transpose_and_merge: reshape groups do not align with permuted dims")
     dst_base = sln0 + (lo * nstr).sum(axis=1)
     recs, rank = _pack(slo0, dst_base, P, sstr, dstr)
-    return recs, rank, int(P.prod(axis=1).sum())
+    covered = int(P.prod(axis=1).sum())
+    if zero_records:
+        hi = mrg[:, T + 2 + r + 1:T + 2 + r + 2 * g:2]
+        zrec, nzero = _zero_records(grp, lo, hi, new[:, T:T + g], new[:, T + g], rank)
+        if zrec is not None and zrec.shape[0]:
+            recs = np.ascontiguousarray(np.vstack([recs, zrec]))
+            covered += nzero
+    return recs, rank, covered
 
 
 def unmerge_records(meta):
@@ -145,7 +209,8 @@ def transpose_records(axes, meta):
 
 
 def reverse_records(recs, rank):
-    """Adjoint copy: swap the source and destination roles of every record."""
+    """Adjoint copy: swap the source and destination roles of every record (zero-fill records have no adjoint)."""
+    recs = recs[recs[:, 0] != SRC_ZERO]
     out = recs.copy()
     out[:, 0], out[:, 1] = recs[:, 1], recs[:, 0]
     out[:, 2 + rank:2 + 2 * rank] = recs[:, 2 + 2 * rank:]
@@ -470,9 +535,9 @@ class CopyPlan:
         self.device = device
 
     def info(self):
-        out = (ctypes.c_int64 * 4)()
+        out = (ctypes.c_int64 * 5)()
         _lib.check(self._lib.yb_copy_plan_info(self.handle, out))
-        return {"items": out[0], "elements": out[1], "records": out[2], "tiled_records": out[3]}
+        return {"items": out[0], "elements": out[1], "records": out[2], "tiled_records": out[3], "runs": out[4]}
 
     def run(self, src_ptr, dst_ptr, dst_elems, flags, stream):
         rc = self._lib.yb_copy_run(self.handle, src_ptr, dst_ptr, dst_elems, flags, stream)
