@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define YB_ABI_VERSION 2
+#define YB_ABI_VERSION 3
 
 /* element types */
 #define YB_F64 0
@@ -96,6 +96,39 @@ int yb_gemm_plan_create_scatter(const int64_t* problems, int64_t nprob, const in
 int yb_gemm_plan_info(const yb_gemm_plan* plan, int64_t info[8]);
 int yb_gemm_run(const yb_gemm_plan* plan, const void* A, const void* B, void* C, int flags, void* stream);
 void yb_gemm_plan_destroy(yb_gemm_plan* plan);
+
+/* ------------------------------------------------------------------------------------------------
+ * Block-wise elementwise plans: the per-block loops of the reference's vector operations, one launch each.
+ *   reference interfaces replaced: backend.add / sub        yastn/backend/backend_torch.py:518-534
+ *                                  backend.negate_blocks    yastn/backend/_backend_torch_backwards.py:229-248
+ *                                  backend.dot_diag         yastn/backend/backend_torch.py:557-564
+ *                                  backend.apply_mask / embed_mask (and backwards)   _backend_torch_backwards.py:251-310
+ *                                  backend.trace            yastn/backend/backend_torch.py:268-275
+ * recs is an nrec x 16 row-major int64 table (units: elements)
+ *     [0] mode  [1] dst  [2] n  [3..6] src offsets (YB_EW_ABSENT: no such source)  [7] negate mask  [8] aux  [9] post  [10] naxis  [11] nfull
+ *   mode 0 LINCOMB  dst[d + i] = sum_k (+/-) src_k[s_k + i]                          i < n; bit k of [7] negates source k
+ *   mode 1 DIAG     dst[d + e] = src_0[s_0 + e] * aux[a + (e / post) % naxis]          e < n; aux has the element type
+ *   mode 2 GATHER   dst[d + e] = src_0[s_0 + (p * nfull + idx[a + j]) * post + q]      e = (p * naxis + j) * post + q < n; aux = int64 idx
+ *   mode 3 SCATTER  dst[d + (p * nfull + idx[a + j]) * post + q] = src_0[s_0 + e]      same decomposition of e
+ *   mode 4 TRACE    dst[d + e] = sum over rows c in [a, a + nfull) of `traces`, sum_{i < D_c} src_0[base_c + i * dstride_c + off_c(e)]
+ *                   with off_c(e) = sum_k idx_k * stride_k for the row-major decomposition of e over ext_c[0..nd_c)
+ * traces is an ntrace x 16 int64 table [0] base [1] D [2] dstride [3] nd [4..9] ext [10..15] stride.
+ * Destination ranges of different records must be disjoint; dst may alias a source (same index in, same index out).
+ * ---------------------------------------------------------------------------------------------- */
+#define YB_EW_ABSENT INT64_MIN
+#define YB_EW_LINCOMB 0
+#define YB_EW_DIAG 1
+#define YB_EW_GATHER 2
+#define YB_EW_SCATTER 3
+#define YB_EW_TRACE 4
+typedef struct yb_ew_plan yb_ew_plan;
+int yb_ew_plan_create(const int64_t* recs, int64_t nrec, const int64_t* traces, int64_t ntrace, int itemsize, int device,
+                      yb_ew_plan** out);
+/* info[0]=work pieces, [1]=elements of the iteration space */
+int yb_ew_plan_info(const yb_ew_plan* plan, int64_t info[2]);
+int yb_ew_run(const yb_ew_plan* plan, void* dst, const void* src0, const void* src1, const void* src2, const void* src3,
+              const void* aux, void* stream);
+void yb_ew_plan_destroy(yb_ew_plan* plan);
 
 /* ------------------------------------------------------------------------------------------------
  * Device-side sector matching (meta pass).  All pointers are DEVICE pointers.  A blocks (table order = the reference's

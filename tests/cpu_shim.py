@@ -11,7 +11,7 @@ import ctypes
 import numpy as np
 import torch
 
-from table_exec import exec_copy, exec_gemm
+from table_exec import exec_copy, exec_gemm, exec_ew
 from yastn_b200 import backend_b200 as bk
 from yastn_b200 import plans, yastn_backend, _lib
 
@@ -74,14 +74,73 @@ class CpuGemmPlan:
         exec_gemm(self.problems, self.segments, A, B, C, bool(flags & _lib.YB_GEMM_CONJ_A), bool(flags & _lib.YB_GEMM_CONJ_B), self.scatter)
 
 
+class CpuEwPlan:
+    """Elementwise plans on CPU tensors: the run call gets raw pointers, so the extents of the views are derived from the
+    records (sources and destination are addressed exactly as the kernel would)."""
+
+    def __init__(self, recs, itemsize, device, traces=None):
+        self.recs = np.ascontiguousarray(recs, dtype=np.int64).reshape(-1, 16)
+        self.traces = np.zeros((0, 16), dtype=np.int64) if traces is None else np.ascontiguousarray(traces, dtype=np.int64).reshape(-1, 16)
+        self.itemsize = itemsize
+
+    def run(self, dst_ptr, src_ptrs, aux_ptr, stream):
+        ABSENT = np.iinfo(np.int64).min
+        big = 1 << 40      # views are created lazily large: only touched indices are accessed
+
+        def ext_dst():
+            m = 0
+            for r in self.recs:
+                mode, d, n = int(r[0]), int(r[1]), int(r[2])
+                if mode == 3:
+                    post, naxis, nfull = max(int(r[9]), 1), max(int(r[10]), 1), int(r[11])
+                    pre = n // (post * naxis) if post * naxis else 0
+                    m = max(m, d + pre * nfull * post)
+                else:
+                    m = max(m, d + n)
+            return m
+        dst = _view(dst_ptr, ext_dst(), self.itemsize)
+        srcs = []
+        for k in range(4):
+            p = src_ptrs[k] if k < len(src_ptrs) else None
+            if p is None:
+                srcs.append(None)
+                continue
+            m = 0
+            for r in self.recs:
+                mode, n, off = int(r[0]), int(r[2]), int(r[3 + k])
+                if off == ABSENT and mode == 0:
+                    continue
+                if mode in (0, 1, 3):
+                    m = max(m, off + n)
+                elif mode == 2:
+                    post, naxis, nfull = max(int(r[9]), 1), max(int(r[10]), 1), int(r[11])
+                    m = max(m, off + (n // (post * naxis)) * nfull * post)
+                else:
+                    for row in self.traces[int(r[8]):int(r[8]) + int(r[11])]:
+                        nd = int(row[3])
+                        m = max(m, int(row[0]) + (int(row[1]) - 1) * int(row[2]) + int(((row[4:4 + nd] - 1) * row[10:10 + nd]).sum()) + 1)
+            srcs.append(_view(p, m, self.itemsize))
+        aux = None
+        if aux_ptr is not None:
+            modes = set(int(r[0]) for r in self.recs)
+            na = max((int(r[8]) + max(int(r[10]), 1) for r in self.recs), default=0)
+            if modes & {2, 3}:
+                buf = (ctypes.c_int64 * na).from_address(aux_ptr)
+                aux = np.ctypeslib.as_array(buf)
+            else:
+                aux = _view(aux_ptr, na, self.itemsize)
+        exec_ew(self.recs, self.traces, dst, srcs, aux)
+
+
 _saved = {}
 
 
 def install():
     if _saved:
         return
-    _saved.update(CopyPlan=plans.CopyPlan, GemmPlan=plans.GemmPlan, on_device=bk._on_device, check=bk._check, native=yastn_backend._native)
-    plans.CopyPlan, plans.GemmPlan = CpuCopyPlan, CpuGemmPlan
+    _saved.update(CopyPlan=plans.CopyPlan, GemmPlan=plans.GemmPlan, EwPlan=plans.EwPlan, on_device=bk._on_device, check=bk._check,
+                  native=yastn_backend._native, on_gpu=yastn_backend._on_gpu)
+    plans.CopyPlan, plans.GemmPlan, plans.EwPlan = CpuCopyPlan, CpuGemmPlan, CpuEwPlan
     bk._on_device = lambda dev, launch: launch(None)
 
     def check(t, name):
@@ -89,13 +148,15 @@ def install():
             raise TypeError(f"yastn_b200.{name}: dtype {t.dtype} not supported (float64 / complex128 only)")
     bk._check = check
     yastn_backend._native = lambda *ts: all(t.dtype in (torch.float64, torch.complex128) for t in ts)
+    yastn_backend._on_gpu = yastn_backend._native
     bk.clear_plan_cache()
 
 
 def uninstall():
     if not _saved:
         return
-    plans.CopyPlan, plans.GemmPlan = _saved["CopyPlan"], _saved["GemmPlan"]
+    plans.CopyPlan, plans.GemmPlan, plans.EwPlan = _saved["CopyPlan"], _saved["GemmPlan"], _saved["EwPlan"]
     bk._on_device, bk._check, yastn_backend._native = _saved["on_device"], _saved["check"], _saved["native"]
+    yastn_backend._on_gpu = _saved["on_gpu"]
     bk.clear_plan_cache()
     _saved.clear()

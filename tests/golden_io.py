@@ -34,6 +34,28 @@ def small_calls():
     return _cache["small"]
 
 
+def ewise_calls():
+    """Recorded calls of add / sub / negate_blocks / dot_diag / apply_mask / embed_mask / trace (make_golden_ewise.py):
+    dict(fn, case, sym, dtype, args{name: value}, out); ``mask`` arguments come back as {charge tuple: int64 index array},
+    lists of arrays (the operands of ``add``) as tuples of arrays."""
+    if "ewise" not in _cache:
+        with gzip.open(os.path.join(GOLDEN, "calls_ewise.json.gz"), "rt") as f:
+            index = json.load(f)
+        arrays = np.load(os.path.join(GOLDEN, "calls_ewise.npz"))
+
+        def get(val):
+            if isinstance(val, str) and val.startswith("@"):
+                return arrays[val[1:]]
+            if isinstance(val, dict) and "__mask__" in val:
+                return {tup(k): arrays[v[1:]] for k, v in val["__mask__"]}
+            if isinstance(val, dict) and "__arrays__" in val:
+                return tuple(arrays[v[1:]] for v in val["__arrays__"])
+            return tup(val)
+        _cache["ewise"] = [{**{x: e[x] for x in ("fn", "case", "sym", "dtype")}, "args": {n: get(v) for n, v in e["args"].items()},
+                            "out": arrays[f"c{k}_out"]} for k, e in enumerate(index)]
+    return _cache["ewise"]
+
+
 def bench_structs():
     """Dict name -> structure fixture (operand block tables, recorded metas per policy, result structure)."""
     if "bench" not in _cache:

@@ -48,3 +48,45 @@ def exec_gemm(problems, segments, A, B, C, conj_a=False, conj_b=False, scatter=N
         else:
             C[offC + m * ldc + n] = acc
     return C
+
+
+def exec_ew(recs, traces, dst, srcs, aux):
+    """Block-wise elementwise records (yb_ew_plan_create in include/yastn_b200.h)."""
+    ABSENT = np.iinfo(np.int64).min
+    for rec in recs:
+        mode, d, n = int(rec[0]), int(rec[1]), int(rec[2])
+        soff, neg, a, post, naxis, nfull = rec[3:7], int(rec[7]), int(rec[8]), max(int(rec[9]), 1), max(int(rec[10]), 1), int(rec[11])
+        if n == 0:
+            continue
+        e = np.arange(n)
+        if mode == 0:
+            acc = np.zeros(n, dtype=dst.dtype)
+            for k in range(4):
+                if soff[k] != ABSENT:
+                    x = srcs[k][int(soff[k]):int(soff[k]) + n]
+                    acc = acc - x if (neg >> k) & 1 else acc + x
+            dst[d:d + n] = acc
+        elif mode == 1:
+            j = (e // post) % naxis
+            dst[d:d + n] = srcs[0][int(soff[0]):int(soff[0]) + n] * aux[a + j]
+        elif mode in (2, 3):
+            q, t = e % post, e // post
+            j, p = t % naxis, t // naxis
+            other = (p * nfull + aux[a + j]) * post + q
+            if mode == 2:
+                dst[d:d + n] = srcs[0][int(soff[0]) + other]
+            else:
+                dst[d + other] = srcs[0][int(soff[0]):int(soff[0]) + n]
+        else:
+            acc = np.zeros(n, dtype=dst.dtype)
+            for row in traces[a:a + nfull]:
+                base, D, ds, nd = int(row[0]), int(row[1]), int(row[2]), int(row[3])
+                ext, st = row[4:4 + nd], row[10:10 + nd]
+                rem, off = e.copy(), np.full(n, base, dtype=np.int64)
+                for k in range(nd - 1, -1, -1):
+                    off += (rem % ext[k]) * st[k]
+                    rem //= ext[k]
+                for i in range(D):
+                    acc += srcs[0][off + i * ds]
+            dst[d:d + n] = acc
+    return dst

@@ -301,6 +301,56 @@ def test_clear_cache_also_drops_plans(device):
     assert our.backend.plan_cache_stats()["size"] == 0
 
 
+@pytest.mark.parametrize("dtype", ["float64", "complex128"])
+def test_vector_ops_run_on_the_elementwise_engine(device, dtype):
+    """SURVEY 8f rows 2-3 through the real YASTN: add / sub / linear combinations, broadcast (dot_diag), apply_mask, trace,
+    svd_with_truncation (apply_mask on U, S, V) against the numpy backend; the calls are counted as native."""
+    ref, our = cfgs("U1", "fuse_to_matrix", device)
+    ref.backend.random_seed(21)
+    leg = yastn.Leg(ref, s=1, t=(-1, 0, 1), D=(4, 5, 6))
+    l2 = yastn.Leg(ref, s=1, t=(-1, 0, 2), D=(2, 3, 4))
+    a = yastn.rand(ref, legs=[leg.conj(), l2, leg, l2.conj()], dtype=dtype)
+    b = yastn.rand(ref, legs=[leg.conj(), l2, leg, l2.conj()], dtype=dtype)
+    c = yastn.Tensor(config=ref, s=a.struct.s, dtype=dtype)
+    c.set_block(ts=(0, 0, 0, 0), Ds=(5, 3, 5, 3), val='rand')
+    c.set_block(ts=(1, -1, 1, -1), Ds=(6, 2, 6, 2), val='rand')
+    d = yastn.rand(ref, legs=[leg.conj(), leg], isdiag=True, dtype=dtype)
+    m = yastn.rand(ref, legs=[leg.conj(), leg], isdiag=True, dtype="float64") > 0.
+    A, B, C, D, M = (mirror(x, our) for x in (a, b, c, d, m))
+    n0 = dict(yastn_backend.call_counts()["native"])
+    close(A + B, a + b)
+    close(A - C, a - c)
+    close(yastn.add(A, B, C, A, B, amplitudes=(1, -2, 0.5, None, 3)), yastn.add(a, b, c, a, b, amplitudes=(1, -2, 0.5, None, 3)), tol=1e-13)
+    close(yastn.broadcast(D, A, axes=2), yastn.broadcast(d, a, axes=2), tol=1e-13)
+    close(yastn.apply_mask(M, A, axes=0), yastn.apply_mask(m, a, axes=0))
+    close(yastn.trace(A, axes=(0, 2)), yastn.trace(a, axes=(0, 2)), tol=1e-13)
+    close(yastn.trace(A, axes=((0, 1), (2, 3))), yastn.trace(a, axes=((0, 1), (2, 3))), tol=1e-13)
+    n1 = yastn_backend.call_counts()["native"]
+    for name in ("add", "sub", "dot_diag", "apply_mask", "trace"):
+        assert n1[name] > n0[name], name
+    U, S, V = yastn.svd_with_truncation(A, axes=((0, 1), (2, 3)), D_total=9)
+    u, s, v = yastn.svd_with_truncation(a, axes=((0, 1), (2, 3)), D_total=9)
+    close(S, s, tol=1e-12)
+    close(U @ S @ V, u @ s @ v, tol=1e-11)
+
+
+def test_swap_gate_negates_blocks_natively(device):
+    """Fermionic swap gates (negate_blocks; every CTM move of a fermionic PEPS): one launch, bit-exact."""
+    ref = yastn.make_config(sym="Z2", backend="np", fermionic=True)
+    our = yastn.make_config(sym="Z2", backend=yastn_backend.module(), fermionic=True, default_device=device)
+    ref.backend.random_seed(4)
+    l1 = yastn.Leg(ref, s=1, t=(0, 1), D=(3, 4))
+    l2 = yastn.Leg(ref, s=1, t=(0, 1), D=(2, 5))
+    a = yastn.rand(ref, legs=[l1.conj(), l2, l1, l2.conj()], n=1, dtype="float64")
+    A = mirror(a, our)
+    n0 = yastn_backend.call_counts()["native"]["negate_blocks"]
+    for axes in ((0, 1), ((0, 1), (2, 3)), (0, 2, 1, 3)):
+        x, y = A.swap_gate(axes=axes), a.swap_gate(axes=axes)
+        same_structure(x, y)
+        assert np.array_equal(x.to_numpy(), y.to_numpy())
+    assert yastn_backend.call_counts()["native"]["negate_blocks"] == n0 + 3
+
+
 def test_dmrg_heisenberg_small(device):
     """Config 1 (reduced): U(1) Heisenberg chain 2-site DMRG runs unmodified on our backend and reproduces the
     energy of the reference numpy backend (reference: tests/mps/test_dmrg.py, yastn/tn/mps/_dmrg.py:42-249)."""

@@ -25,6 +25,10 @@ SIGNATURES = {
     "yb_gemm_plan_info": (_c.c_int, [_vp, _i64p]),
     "yb_gemm_run": (_c.c_int, [_vp, _vp, _vp, _vp, _c.c_int, _vp]),
     "yb_gemm_plan_destroy": (None, [_vp]),
+    "yb_ew_plan_create": (_c.c_int, [_vp, _c.c_int64, _vp, _c.c_int64, _c.c_int, _c.c_int, _c.POINTER(_vp)]),
+    "yb_ew_plan_info": (_c.c_int, [_vp, _i64p]),
+    "yb_ew_run": (_c.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "yb_ew_plan_destroy": (None, [_vp]),
     "yb_peer_alloc": (_c.c_int, [_c.c_int64, _c.c_int, _c.POINTER(_vp), _vp]),
     "yb_peer_open": (_c.c_int, [_vp, _c.c_int, _c.POINTER(_vp)]),
     "yb_peer_close": (_c.c_int, [_vp]),
@@ -33,7 +37,7 @@ SIGNATURES = {
     "yb_match_sectors": (_c.c_int, [_vp, _vp, _vp, _c.c_int64, _vp, _vp, _vp, _c.c_int64, _c.c_int, _c.c_int64, _vp, _vp, _vp, _vp, _vp]),
 }
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 YB_F64, YB_C128 = 0, 1
 YB_COPY_ZERO_DST, YB_COPY_CONJ = 1, 2
 YB_GEMM_CONJ_A, YB_GEMM_CONJ_B = 1, 2

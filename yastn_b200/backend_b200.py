@@ -492,6 +492,199 @@ def vdot(Adata, Bdata, meta):
     return torch.sum(tmp)
 
 
+# -------------------------------------------------------------------------------------------------
+# block-wise elementwise operations: one launch each instead of a Python loop over blocks
+# -------------------------------------------------------------------------------------------------
+
+def _run_ew(plan, dst, srcs, aux=None):
+    _on_device(dst.device, lambda st: plan.run(dst.data_ptr(), [s.data_ptr() for s in srcs], None if aux is None else aux.data_ptr(), st))
+
+
+def _plain(t, dtype):
+    """Contiguous tensor of ``dtype`` with the conj bit resolved (elementwise kernels read raw storage)."""
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    if t.is_conj():
+        t = t.resolve_conj()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _lincomb(datas, metas, Dsize, signs, name):
+    for d in datas:
+        _check(d, name)
+    dtype = datas[0].dtype
+    for d in datas[1:]:
+        dtype = torch.promote_types(dtype, d.dtype)
+    dev = datas[0].device
+    key = (name, id(metas), signs, dtype, dev.index)
+
+    def build():
+        rounds = plans.add_tables(metas, signs)
+        covered = sum(hi - lo for (lo, hi) in {sl_c for meta in metas for (sl_c, _) in meta})
+        return {"rounds": [(plans.EwPlan(recs, _ITEMSIZE[dtype], dev.index), slots) for recs, slots in rounds], "covered": covered}
+    ent = _CACHE.get(key, metas, build)
+    datas = [_plain(d, dtype) for d in datas]
+    # the reference starts from zeros; every output block is written by at least one operand, so only gaps would need them
+    out = torch.empty(Dsize, dtype=dtype, device=dev) if ent["covered"] >= Dsize else torch.zeros(Dsize, dtype=dtype, device=dev)
+    for plan, slots in ent["rounds"]:
+        _run_ew(plan, out, [out if k < 0 else datas[k] for k in slots])
+    return out
+
+
+def add(datas, metas, Dsize):
+    """``sum_k datas[k]`` block by block (yastn/backend/backend_torch.py:518-524): one launch for up to four operands."""
+    return _lincomb(list(datas), metas, Dsize, (1,) * len(datas), "add")
+
+
+def sub(Adata, Bdata, metas, Dsize):
+    """``Adata - Bdata`` block by block (yastn/backend/backend_torch.py:527-534)."""
+    return _lincomb([Adata, Bdata], metas, Dsize, (1, -1), "sub")
+
+
+def _negate_forward(Adata, slices):
+    key = ("neg", id(slices), Adata.numel(), Adata.dtype, Adata.device.index)
+
+    def build():
+        return {"fwd": plans.EwPlan(plans.negate_tables(slices, Adata.numel()), _ITEMSIZE[Adata.dtype], Adata.device.index)}
+    ent = _CACHE.get(key, slices, build)
+    A = _plain(Adata, Adata.dtype)
+    out = torch.empty_like(A)
+    _run_ew(ent["fwd"], out, [A])
+    return out
+
+
+class _NegateBlocks(torch.autograd.Function):
+    @staticmethod
+    def forward(Adata, slices):
+        return _negate_forward(Adata, slices)
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        ctx.slices = inputs[1]
+
+    @staticmethod
+    def backward(ctx, grad):
+        return _negate_forward(grad, ctx.slices), None
+
+
+def negate_blocks(Adata, slices):
+    """Copy of ``Adata`` with the listed blocks multiplied by -1 (yastn/backend/_backend_torch_backwards.py:229-248; every
+    fermionic ``swap_gate``): one launch instead of a clone plus one in-place multiply per block."""
+    _check(Adata, "negate_blocks")
+    if _needs_grad(Adata):
+        return _NegateBlocks.apply(Adata, slices)
+    return _negate_forward(Adata, slices)
+
+
+def dot_diag(Adata, Bdata, meta, Dsize, axis, a_ndim):
+    """Diagonal tensor times one leg of a tensor (yastn/backend/backend_torch.py:557-564, ``yastn.broadcast``): one launch.
+    Forward only (the YASTN module hands inputs that require grad to the reference's differentiable loop)."""
+    _check(Adata, "dot_diag")
+    _check(Bdata, "dot_diag")
+    dtype = torch.promote_types(Adata.dtype, Bdata.dtype)
+    dev = Bdata.device
+    key = ("ddiag", id(meta), axis, a_ndim, dtype, dev.index)
+
+    def build():
+        return {"fwd": plans.EwPlan(plans.dot_diag_tables(meta, axis, a_ndim), _ITEMSIZE[dtype], dev.index)}
+    ent = _CACHE.get(key, meta, build)
+    out = torch.empty(Dsize, dtype=dtype, device=dev)
+    _run_ew(ent["fwd"], out, [_plain(Bdata, dtype)], _plain(Adata, dtype))
+    return out
+
+
+def _mask_index(mask, order, device):
+    idx = [mask[tm] for tm in order]
+    idx = [torch.as_tensor(v, device=device).to(torch.int64).reshape(-1) for v in idx]
+    return idx[0].contiguous() if len(idx) == 1 else torch.cat(idx)
+
+
+def _mask_run(data, mask, meta, Dsize, axis, ndim, scatter):
+    """GATHER (scatter=False) / SCATTER (True) of the records of ``meta``; SCATTER leaves the unselected positions zero."""
+    key = ("mask", id(meta), axis, ndim, scatter, data.dtype, data.device.index)
+
+    def build():
+        recs, order = plans.mask_tables(meta, axis, ndim, scatter)
+        return {"fwd": plans.EwPlan(recs, _ITEMSIZE[data.dtype], data.device.index), "order": order}
+    ent = _CACHE.get(key, meta, build)
+    out = (torch.zeros if scatter else torch.empty)(Dsize, dtype=data.dtype, device=data.device)
+    if len(meta):
+        _run_ew(ent["fwd"], out, [_plain(data, data.dtype)], _mask_index(mask, ent["order"], data.device))
+    return out
+
+
+def _swap_meta(meta):
+    """Records of the adjoint: source and destination blocks trade places."""
+    return tuple((sla, Da, sln, Dn, tm) for sln, Dn, sla, Da, tm in meta)
+
+
+class _ApplyMask(torch.autograd.Function):
+    @staticmethod
+    def forward(Adata, mask, meta, Dsize, axis, ndim):
+        return _mask_run(Adata, mask, meta, Dsize, axis, ndim, scatter=False)
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        Adata, ctx.mask, ctx.meta, _, ctx.axis, ctx.ndim = inputs
+        ctx.n = Adata.numel()
+
+    @staticmethod
+    def backward(ctx, grad):
+        key = ("maskadj", id(ctx.meta))
+        adj = _CACHE.get(key, ctx.meta, lambda: _swap_meta(ctx.meta))
+        return _mask_run(grad, ctx.mask, adj, ctx.n, ctx.axis, ctx.ndim, scatter=True), None, None, None, None, None
+
+
+class _EmbedMask(torch.autograd.Function):
+    @staticmethod
+    def forward(Adata, mask, meta, Dsize, axis, ndim):
+        return _mask_run(Adata, mask, meta, Dsize, axis, ndim, scatter=True)
+
+    @staticmethod
+    def setup_context(ctx, inputs, output):
+        Adata, ctx.mask, ctx.meta, _, ctx.axis, ctx.ndim = inputs
+        ctx.n = Adata.numel()
+
+    @staticmethod
+    def backward(ctx, grad):
+        key = ("maskadj", id(ctx.meta))
+        adj = _CACHE.get(key, ctx.meta, lambda: _swap_meta(ctx.meta))
+        out = _mask_run(grad, ctx.mask, adj, ctx.n, ctx.axis, ctx.ndim, scatter=False)
+        return out, None, None, None, None, None
+
+
+def apply_mask(Adata, mask, meta, Dsize, axis, ndim):
+    """Keep the positions ``mask[tm]`` along one leg of every block (yastn/backend/_backend_torch_backwards.py:251-279; the
+    truncation after every SVD): one gather launch (+ one ``cat`` of the index vectors) instead of an index-select per block."""
+    _check(Adata, "apply_mask")
+    if _needs_grad(Adata):
+        return _ApplyMask.apply(Adata, mask, meta, Dsize, axis, ndim)
+    return _mask_run(Adata, mask, meta, Dsize, axis, ndim, scatter=False)
+
+
+def embed_mask(Adata, mask, meta, Dsize, axis, ndim):
+    """Inverse placement: blocks go to the positions ``mask[tm]`` of a zero tensor (:282-310)."""
+    _check(Adata, "embed_mask")
+    if _needs_grad(Adata):
+        return _EmbedMask.apply(Adata, mask, meta, Dsize, axis, ndim)
+    return _mask_run(Adata, mask, meta, Dsize, axis, ndim, scatter=True)
+
+
+def trace(data, order, meta, Dsize):
+    """Partial trace over pairs of legs (yastn/backend/backend_torch.py:268-275): one launch.  Forward only."""
+    _check(data, "trace")
+    key = ("trace", id(meta), tuple(order), data.dtype, data.device.index)
+
+    def build():
+        recs, traces = plans.trace_tables(order, meta)
+        covered = sum(sln[1] - sln[0] for sln, _ in meta)
+        return {"fwd": plans.EwPlan(recs, _ITEMSIZE[data.dtype], data.device.index, traces), "covered": covered}
+    ent = _CACHE.get(key, meta, build)
+    out = (torch.empty if ent["covered"] >= Dsize else torch.zeros)(Dsize, dtype=data.dtype, device=data.device)
+    _run_ew(ent["fwd"], out, [_plain(data, data.dtype)])
+    return out
+
+
 _BS_CACHE = plans.PlanCache(maxsize=1024)
 
 

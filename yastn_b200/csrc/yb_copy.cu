@@ -752,11 +752,11 @@ extern "C" int yb_copy_plan_create(const int64_t* recs, int64_t nrec, int rank, 
         on_runs[i] = 1;
         for (int64_t r = 0; r < rows; ++r) {
             const int64_t so = h.src_base + (h.nd == 2 ? r * h.sstr[0] : 0), dof = h.dst_base + (h.nd == 2 ? r * h.dstr[0] : 0);
-            for (int64_t c = 0; c < L; c += kRunPiece) {
+            for (int64_t c = 0; c < L; c += item_elems) {     // pieces of one work item's size: small tensors stay spread out
                 CopyRun run;
                 run.src = so + c;
                 run.dst = dof + c;
-                run.n = (uint32_t)std::min<int64_t>(kRunPiece, L - c);
+                run.n = (uint32_t)std::min<int64_t>(item_elems, L - c);
                 run.flags = 0u;
                 run.pad_[0] = run.pad_[1] = 0;
                 runs.push_back(run);
@@ -769,7 +769,7 @@ extern "C" int yb_copy_plan_create(const int64_t* recs, int64_t nrec, int rank, 
         while (b < runs.size()) {
             size_t e = b;
             uint64_t acc = 0;
-            while (e < runs.size() && e - b < (size_t)kRunBatch && (acc == 0 || acc + runs[e].n <= std::max<uint32_t>(item_elems, 1024))) acc += runs[e++].n;
+            while (e < runs.size() && e - b < (size_t)kRunBatch && (acc == 0 || acc + runs[e].n <= item_elems)) acc += runs[e++].n;
             CopyItem it = {(int32_t)b, (int32_t)e, 0, 0, 5, {0, 0, 0}};
             items.push_back(it);
             b = e;

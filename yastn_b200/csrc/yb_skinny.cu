@@ -350,45 +350,53 @@ int skinny_create(const std::vector<GemmProblem>& hp, const std::vector<GemmSegm
     int rc0 = cplx ? occupancy_x<true>(plan->xt, plan->yt, &occ) : occupancy_x<false>(plan->xt, plan->yt, &occ);
     if (rc0 != kOk || occ < 1) occ = 1;
     const int64_t max_warps = (int64_t)sms * kSkWarps * occ;
-    const int64_t chunk = std::max<int64_t>(kSkMinChunk, (W + max_warps - 1) / max_warps);
-
+    // shares: cut the work line into pieces of `chunk` weight.  Every warp of the grid must be resident at once (a second,
+    // partial wave doubles the run time of this latency-bound kernel: 607 CTAs on 592 slots cost 2x in the first version),
+    // so the chunk grows until the number of shares fits.
+    int64_t chunk = std::max<int64_t>(kSkMinChunk, (W + max_warps - 1) / max_warps);
     std::vector<SkPart> parts;
     std::vector<SkWarp> warps;
-    std::vector<SkRuns> runs((size_t)plan->nlp, SkRuns{-1, -1});
-    int64_t cur = 0;
-    int warp_begin = 0;
-    auto close_warp = [&]() {
-        if ((int)parts.size() > warp_begin) {
-            warps.push_back({warp_begin, (int)parts.size()});
-            warp_begin = (int)parts.size();
-        }
-        cur = 0;
-    };
-    for (int lp = 0; lp < plan->nlp; ++lp) {
-        const int idx = which[(size_t)lp];
-        const GemmProblem& P = hp[(size_t)idx];
-        const int64_t per = std::max(1, P.M + P.N);
-        bool any = false;
-        for (int s = P.seg_begin; s < P.seg_end; ++s) {
-            const int64_t K = hs[(size_t)s].K;
-            int64_t c = 0;
-            while (c < K) {
+    for (int attempt = 0; attempt < 16; ++attempt) {
+        parts.clear();
+        warps.clear();
+        int64_t cur = 0;
+        int warp_begin = 0;
+        auto close_warp = [&]() {
+            if ((int)parts.size() > warp_begin) {
+                warps.push_back({warp_begin, (int)parts.size()});
+                warp_begin = (int)parts.size();
+            }
+            cur = 0;
+        };
+        for (int lp = 0; lp < plan->nlp; ++lp) {
+            const int idx = which[(size_t)lp];
+            const GemmProblem& P = hp[(size_t)idx];
+            const int64_t per = std::max(1, P.M + P.N);
+            bool any = false;
+            for (int s = P.seg_begin; s < P.seg_end; ++s) {
+                const int64_t K = hs[(size_t)s].K;
+                int64_t c = 0;
+                while (c < K) {
+                    if (cur + kSkPartOverhead >= chunk) close_warp();
+                    const int64_t room = chunk - cur - kSkPartOverhead;
+                    const int64_t take = std::min(K - c, std::max<int64_t>(32, room / per));
+                    parts.push_back({idx, lp, s, (int32_t)c, (int32_t)(c + take), 0, 0, 0});
+                    any = true;
+                    cur += take * per + kSkPartOverhead;
+                    c += take;
+                }
+            }
+            if (!any) {   // nothing to contract: the block is zero
                 if (cur + kSkPartOverhead >= chunk) close_warp();
-                const int64_t room = chunk - cur - kSkPartOverhead;
-                const int64_t take = std::min(K - c, std::max<int64_t>(32, room / per));
-                parts.push_back({idx, lp, s, (int32_t)c, (int32_t)(c + take), 0, 0, 0});
-                any = true;
-                cur += take * per + kSkPartOverhead;
-                c += take;
+                parts.push_back({idx, lp, -1, 0, 0, 0, 0, 0});
+                cur += kSkPartOverhead;
             }
         }
-        if (!any) {   // nothing to contract: the block is zero
-            if (cur + kSkPartOverhead >= chunk) close_warp();
-            parts.push_back({idx, lp, -1, 0, 0, 0, 0, 0});
-            cur += kSkPartOverhead;
-        }
+        close_warp();
+        if ((int64_t)warps.size() <= max_warps) break;
+        chunk = chunk + chunk / 16 + 64;
     }
-    close_warp();
+    std::vector<SkRuns> runs((size_t)plan->nlp, SkRuns{-1, -1});
     // runs: maximal sequences of parts of one problem inside one warp
     int nruns = 0;
     for (const SkWarp& w : warps) {

@@ -513,6 +513,169 @@ def bs_to_tds(a_t, a_slices, nout_a, nin_a, b_t, b_slices, nout_b, nin_b, c_t, c
 
 
 # -------------------------------------------------------------------------------------------------
+# block-wise elementwise tables (include/yastn_b200.h, yb_ew_plan_create)
+# -------------------------------------------------------------------------------------------------
+
+EW_ABSENT = np.iinfo(np.int64).min
+EW_LINCOMB, EW_DIAG, EW_GATHER, EW_SCATTER, EW_TRACE = range(5)
+EW_SOURCES = 4
+
+
+def _ew_rec(mode, dst, n, src=(), neg=0, aux=0, post=1, naxis=1, nfull=0):
+    rec = [mode, dst, n] + list(src) + [EW_ABSENT] * (EW_SOURCES - len(src)) + [neg, aux, post, naxis, nfull, 0, 0, 0, 0]
+    return rec
+
+
+def _ew_array(recs):
+    return np.array(recs, dtype=I64).reshape(len(recs), 16)
+
+
+def add_tables(metas, signs=None):
+    """Rounds of LINCOMB records of backend.add / sub (yastn/backend/backend_torch.py:518-534): ``new[sl_c] (+/-)= data_k[sl_a]``
+    for every (sl_c, sl_a) of ``metas[k]``; output ranges no operand writes stay zero (``newdata = torch.zeros``).
+
+    One launch adds up to four operands; with more, later rounds read the running sum as their first source.  Returns a list
+    of (records, operand indices) — operand index -1 is the output itself."""
+    n_ops = len(metas)
+    signs = signs or (1,) * n_ops
+    cuts = sorted({x for meta in metas for (sl_c, _) in meta for x in sl_c})
+    # elementary output intervals and who writes them
+    starts = np.array(cuts[:-1], dtype=I64) if len(cuts) > 1 else np.zeros(0, dtype=I64)
+    writers = [[] for _ in range(max(len(cuts) - 1, 0))]
+    for k, meta in enumerate(metas):
+        for (c0, c1), (a0, a1) in meta:
+            if c1 <= c0:
+                continue
+            i = int(np.searchsorted(starts, c0))
+            while i < len(starts) and starts[i] < c1:
+                writers[i].append((k, a0 + int(starts[i]) - c0))
+                i += 1
+    rounds = []
+    ops_left = list(range(n_ops))
+    first = True
+    while ops_left:
+        take = ops_left[:EW_SOURCES if first else EW_SOURCES - 1]
+        ops_left = ops_left[len(take):]
+        slots = ([] if first else [-1]) + take
+        recs = []
+        for i, w in enumerate(writers):
+            lo, hi = cuts[i], cuts[i + 1]
+            src = [EW_ABSENT] * len(slots)
+            neg = 0
+            hit = False
+            for (k, off) in w:
+                if k in take:
+                    j = slots.index(k)
+                    if src[j] != EW_ABSENT:
+                        raise ValueError("add: an operand writes an output element twice")
+                    src[j] = off
+                    hit = True
+                    if signs[k] < 0:
+                        neg |= 1 << j
+            if not first:
+                if not hit:
+                    continue                      # nothing new for this interval: the running sum stays
+                src[0] = lo
+            elif not w:
+                continue                          # gap between blocks: belongs to no output block
+            recs.append(_ew_rec(EW_LINCOMB, lo, hi - lo, src, neg))
+        rounds.append((_ew_array(recs), slots))
+        first = False
+    return rounds
+
+
+def negate_tables(slices, size):
+    """LINCOMB records of negate_blocks (yastn/backend/_backend_torch_backwards.py:229-248): a copy of the data with the
+    sign of the listed slices flipped."""
+    recs, pos = [], 0
+    for lo, hi in sorted(slices):
+        if lo > pos:
+            recs.append(_ew_rec(EW_LINCOMB, pos, lo - pos, [pos], 0))
+        if hi > lo:
+            recs.append(_ew_rec(EW_LINCOMB, lo, hi - lo, [lo], 1))
+        pos = max(pos, hi)
+    if size > pos:
+        recs.append(_ew_rec(EW_LINCOMB, pos, size - pos, [pos], 0))
+    return _ew_array(recs)
+
+
+def dot_diag_tables(meta, axis, a_ndim):
+    """DIAG records of backend.dot_diag (yastn/backend/backend_torch.py:557-564): ``new[sln].reshape(Db) = A[sla] (along axis) * B[slb].reshape(Db)``."""
+    recs = []
+    for sln, slb, Db, sla in meta:
+        Db = (Db,) if isinstance(Db, int) else tuple(Db)
+        ax = axis if a_ndim > 0 else 0
+        post = int(np.prod(Db[ax + 1:], dtype=I64))
+        recs.append(_ew_rec(EW_DIAG, sln[0], sln[1] - sln[0], [slb[0]], 0, sla[0], post, Db[ax], 0))
+    return _ew_array(recs)
+
+
+def mask_tables(meta, axis, ndim, scatter):
+    """GATHER / SCATTER records of apply_mask / embed_mask (yastn/backend/_backend_torch_backwards.py:251-310).
+
+    meta = ((sln, Dn, sla, Da, tm), ...): apply_mask takes ``A[sla].view(Da)[..., mask[tm], ...]`` into ``C[sln].view(Dn)``
+    (scatter=False, the iteration space is the output block Dn, Da has the full extent); embed_mask puts ``A[sla].view(Da)``
+    into ``C[sln].view(Dn)[..., mask[tm], ...]`` (scatter=True, the iteration space is the input block Da, Dn is full).
+    Returns (records, tm order): the index vectors ``mask[tm]`` are concatenated in that order."""
+    order, aux_of, pos = [], {}, 0
+    recs = []
+    for sln, Dn, sla, Da, tm in meta:
+        small, full = (Da, Dn) if scatter else (Dn, Da)
+        small = (small,) if isinstance(small, int) else tuple(small)
+        full = (full,) if isinstance(full, int) else tuple(full)
+        ax = axis if ndim > 0 else 0
+        nsel = small[ax] if small else 1
+        if tm not in aux_of:
+            aux_of[tm] = pos
+            order.append(tm)
+            pos += nsel
+        post = int(np.prod(small[ax + 1:], dtype=I64))
+        n = int(np.prod(small, dtype=I64))
+        recs.append(_ew_rec(EW_SCATTER if scatter else EW_GATHER, sln[0], n, [sla[0]], 0, aux_of[tm], post, nsel, full[ax] if full else 1))
+    return _ew_array(recs), tuple(order)
+
+
+def trace_tables(order, meta):
+    """TRACE records of backend.trace (yastn/backend/backend_torch.py:268-275):
+    ``new[sln] += sum_i data[slo].reshape(Do).permute(order).reshape(D, D, rest)[i, i, :]``."""
+    recs, traces = [], []
+    order = list(order)
+    for sln, lst in meta:
+        first = len(traces)
+        for slo, Do, Drsh in lst:
+            st = _cstrides(np.array([Do], dtype=I64))[0]
+            P = [Do[k] for k in order]
+            ps = [int(st[k]) for k in order]
+            # leading permuted dims form the two traced groups (products Drsh[0] == Drsh[1]); the rest is the output index
+            split0, prod = 0, 1
+            while prod != Drsh[0]:
+                prod *= P[split0]
+                split0 += 1
+            split1, prod = split0, 1
+            while prod != Drsh[1]:
+                prod *= P[split1]
+                split1 += 1
+            g0 = [(e, s) for e, s in zip(P[:split0], ps[:split0]) if e > 1]
+            g1 = [(e, s) for e, s in zip(P[split0:split1], ps[split0:split1]) if e > 1]
+            if [e for e, _ in g0] != [e for e, _ in g1]:
+                raise ValueError("trace: traced leg groups of different shape")
+            rest = [(e, s) for e, s in zip(P[split1:], ps[split1:]) if e > 1]
+            if len(rest) > 6:
+                raise ValueError("trace: more than 6 remaining legs")
+            # the diagonal of a multi-leg group is not a single stride: one trace row per index of all but the last traced leg
+            outer = g0[:-1]
+            outer1 = g1[:-1]
+            D, ds = (g0[-1][0], g0[-1][1] + g1[-1][1]) if g0 else (1, 0)
+            for idx in np.ndindex(*[e for e, _ in outer]) if outer else [()]:
+                base = slo[0] + sum(i * (s0 + s1) for i, (_, s0), (_, s1) in zip(idx, outer, outer1))
+                row = [base, D, ds, len(rest)] + [e for e, _ in rest] + [1] * (6 - len(rest)) + [s for _, s in rest] + [0] * (6 - len(rest))
+                traces.append(row)
+        recs.append(_ew_rec(EW_TRACE, sln[0], sln[1] - sln[0], [0], 0, first, 1, 1, len(traces) - first))
+    tr = np.array(traces, dtype=I64).reshape(len(traces), 16)
+    return _ew_array(recs), tr
+
+
+# -------------------------------------------------------------------------------------------------
 # device plans
 # -------------------------------------------------------------------------------------------------
 
@@ -548,6 +711,37 @@ class CopyPlan:
         try:
             if self.handle:
                 self._lib.yb_copy_plan_destroy(self.handle)
+        except Exception:
+            pass
+
+
+class EwPlan:
+    """Device plan of one block-wise elementwise launch (owns the C handle)."""
+
+    def __init__(self, recs, itemsize, device, traces=None):
+        lib = _lib.load()
+        self._lib = lib
+        self.handle = ctypes.c_void_p()
+        recs = np.ascontiguousarray(recs, dtype=I64).reshape(-1, 16)
+        traces = np.zeros((0, 16), dtype=I64) if traces is None else np.ascontiguousarray(traces, dtype=I64).reshape(-1, 16)
+        _lib.check(lib.yb_ew_plan_create(_ptr(recs), recs.shape[0], _ptr(traces), traces.shape[0], itemsize, device, ctypes.byref(self.handle)))
+        self.itemsize, self.device = itemsize, device
+
+    def info(self):
+        out = (ctypes.c_int64 * 2)()
+        _lib.check(self._lib.yb_ew_plan_info(self.handle, out))
+        return {"pieces": out[0], "elements": out[1]}
+
+    def run(self, dst_ptr, src_ptrs, aux_ptr, stream):
+        p = list(src_ptrs) + [None] * (EW_SOURCES - len(src_ptrs))
+        rc = self._lib.yb_ew_run(self.handle, dst_ptr, p[0], p[1], p[2], p[3], aux_ptr, stream)
+        if rc:
+            _lib.check(rc)
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self._lib.yb_ew_plan_destroy(self.handle)
         except Exception:
             pass
 

@@ -28,10 +28,12 @@ from . import backend_b200 as _bk
 from . import decomp as _decomp
 
 _HOT = _bk.HOT_FUNCTIONS
+_EWISE = ("add", "sub", "negate_blocks", "dot_diag", "apply_mask", "embed_mask", "trace")
 _DECOMP = ("svd", "svdvals", "eigh", "qr")
 _NATIVE = (torch.float64, torch.complex128)
 _state = {"module": {}, "saved": None, "cpu_passthrough": False, "saved_f2m": None, "saved_decomp": None,
-          "calls": {name: 0 for name in _HOT + ("dot_unmerge", "kernel_tensordot_bs", "vdot")}, "delegated": {name: 0 for name in _HOT}}
+          "calls": {name: 0 for name in _HOT + ("dot_unmerge", "kernel_tensordot_bs", "vdot") + _EWISE},
+          "delegated": {name: 0 for name in _HOT + _EWISE}}
 
 
 def _stock():
@@ -53,6 +55,11 @@ def _native(*tensors):
             raise TypeError(f"yastn_b200: CPU tensor reached a hot backend function (device {t.device}); "
                             "this backend has no CPU path — build the config with default_device='cuda'")
     return all(t.dtype in _NATIVE for t in tensors)
+
+
+def _on_gpu(*tensors):
+    """float64 / complex128 CUDA tensors only (the vector operations never raise for other inputs, see ``ewise`` below)."""
+    return all(t.is_cuda and t.dtype in _NATIVE for t in tensors)
 
 
 def _make_hot(stock_fns, delegate):
@@ -118,9 +125,46 @@ def _make_hot(stock_fns, delegate):
         calls["vdot"] += 1
         return _bk.vdot(Adata, Bdata, meta)
 
+    # ---- block-wise elementwise operations.  add / sub / dot_diag / trace are differentiated by torch itself in the
+    # reference (plain tensor ops): inputs that require grad keep that code; negate_blocks / apply_mask / embed_mask carry
+    # their own backward like the reference's autograd.Functions.
+    def _grad(*tensors):
+        return torch.is_grad_enabled() and any(t.requires_grad for t in tensors)
+
+    def ewise(name, tensors, args, needs_forward_only):
+        # these are the reference's general-purpose vector operations (also used on small host-side tensors while a model is
+        # set up): anything that is not a float64 / complex128 CUDA tensor stays with the reference's own code
+        if (needs_forward_only and _grad(*tensors)) or not _on_gpu(*tensors):
+            delegated[name] += 1
+            return stock_fns[name](*args)
+        calls[name] += 1
+        return getattr(_bk, name)(*args)
+
+    def add(datas, metas, Dsize):
+        return ewise("add", tuple(datas), (datas, metas, Dsize), True)
+
+    def sub(Adata, Bdata, metas, Dsize):
+        return ewise("sub", (Adata, Bdata), (Adata, Bdata, metas, Dsize), True)
+
+    def negate_blocks(Adata, slices):
+        return ewise("negate_blocks", (Adata,), (Adata, slices), False)
+
+    def dot_diag(Adata, Bdata, meta, Dsize, axis, a_ndim):
+        return ewise("dot_diag", (Adata, Bdata), (Adata, Bdata, meta, Dsize, axis, a_ndim), True)
+
+    def apply_mask(Adata, mask, meta, Dsize, axis, ndim):
+        return ewise("apply_mask", (Adata,), (Adata, mask, meta, Dsize, axis, ndim), False)
+
+    def embed_mask(Adata, mask, meta, Dsize, axis, ndim):
+        return ewise("embed_mask", (Adata,), (Adata, mask, meta, Dsize, axis, ndim), False)
+
+    def trace(data, order, meta, Dsize):
+        return ewise("trace", (data,), (data, order, meta, Dsize), True)
+
     return {"transpose_and_merge": transpose_and_merge, "unmerge": unmerge, "transpose": transpose, "dot": dot,
             "transpose_dot_sum": transpose_dot_sum, "dot_unmerge": dot_unmerge, "kernel_tensordot_bs": kernel_tensordot_bs,
-            "vdot": vdot}
+            "vdot": vdot, "add": add, "sub": sub, "negate_blocks": negate_blocks, "dot_diag": dot_diag, "apply_mask": apply_mask,
+            "embed_mask": embed_mask, "trace": trace}
 
 
 def _hook_cache_control():
@@ -168,7 +212,7 @@ def module(delegate_other_dtypes=True, bs_boundary=False):
     if variant not in _state["module"]:
         stock = _stock()
         _hook_cache_control()
-        saved = _state["saved"] or {n: getattr(stock, n) for n in _HOT + ("vdot",)}
+        saved = _state["saved"] or {n: getattr(stock, n) for n in _HOT + ("vdot",) + _EWISE}
         mod = types.ModuleType("yastn_b200_backend" + ("_bs" if bs_boundary else ""),
                                "stock yastn torch backend with the B200 contraction kernels")
         for name in dir(stock):
@@ -197,7 +241,7 @@ def activate(delegate_other_dtypes=True, cpu_passthrough=False):
     _hook_cache_control()
     _state["cpu_passthrough"] = bool(cpu_passthrough)
     if _state["saved"] is None:
-        _state["saved"] = {n: getattr(stock, n) for n in _HOT + ("vdot",)}
+        _state["saved"] = {n: getattr(stock, n) for n in _HOT + ("vdot",) + _EWISE}
     for name, fn in _make_hot(_state["saved"], delegate_other_dtypes).items():
         if name in _state["saved"] or name in ("dot_unmerge", "kernel_tensordot_bs"):
             setattr(stock, name, fn)
