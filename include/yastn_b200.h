@@ -87,13 +87,16 @@ int yb_gemm_plan_create_scatter(const int64_t* problems, int64_t nprob, const in
                                 const int64_t* col_ptr, const int64_t* col_cuts, const int64_t* dst_ptr, const int64_t* dst,
                                 int dtype, int device, yb_gemm_plan** out);
 /* info[0]=tiles, [1]=real multiply-adds (M*N*K summed), [2]=big tiles, [3]=small tiles, [4]=grid (CTAs), [5]=CTAs that
- * start inside a tile (stream-K partials), [6]=warps of the skinny-output kernel, [7]=its partial-sum runs.
+ * start inside a tile (stream-K partials), [6]=warps of the skinny-output kernel, [7]=its partial-sum runs, [8]=work units of
+ * the panel kernel, [9]=reserved.
  * Problems whose result block is at most 8 x 8 (complex128: at most 32 entries) are not tiled: they run as HBM-bound
  * reductions over the contraction index in a second kernel of the same yb_gemm_run call (backend.vdot, huge-K / tiny-output
- * contractions, adjoints of tall-and-skinny products); any strides are accepted for them.
+ * contractions, adjoints of tall-and-skinny products); any strides are accepted for them.  Problems with K <= 8 and exactly
+ * one of M, N <= 8 (an MPO block applied to an environment: the other extent runs to 10^7) are streaming products and run in
+ * a third kernel, also with any strides.
  * Cross-CTA scratch (stream-K partial tiles, partial sums) is looked up per (device, stream) at launch time: plans may run
  * concurrently on different streams.  Launches that wait on partial tiles of other CTAs are cooperative launches. */
-int yb_gemm_plan_info(const yb_gemm_plan* plan, int64_t info[8]);
+int yb_gemm_plan_info(const yb_gemm_plan* plan, int64_t info[10]);
 int yb_gemm_run(const yb_gemm_plan* plan, const void* A, const void* B, void* C, int flags, void* stream);
 void yb_gemm_plan_destroy(yb_gemm_plan* plan);
 

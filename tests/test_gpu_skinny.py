@@ -229,3 +229,62 @@ def test_skinny_adjoint_of_tall_products(bk):
         bk.dot(gA, gB, meta, oc).backward(_dev(G))
         ra, rb = orc.dot_backward(G, A, B, meta)
         assert _relerr(gA.grad.cpu().numpy(), ra) <= TOL and _relerr(gB.grad.cpu().numpy(), rb) <= TOL
+
+
+@pytest.mark.parametrize("cplx", [False, True], ids=["f64", "c128"])
+def test_panel_products_all_layouts(cplx):
+    """A tiny matrix times a very long one (K <= 8, one of M, N <= 8: an MPO block applied to an environment), both
+    orientations, every operand layout (row-major and transposed views of either operand, padded leading dimensions), conj
+    flags, two segments per problem, next to tile and skinny problems in the same plan; against the table interpreter."""
+    rng = np.random.default_rng(31)
+    shapes = [(4, 4, 300_003), (1, 3, 50_001), (300_007, 4, 2), (100_001, 1, 8), (8, 8, 70_001), (77_777, 8, 8), (2, 1, 1_000_000),
+              (3, 5, 257), (200, 3, 3), (130, 40, 70), (3, 100_000, 2)]         # the last three: too short / a tile / a skinny problem
+    for variant in range(3):
+        problems, segments = [], []
+        oa, ob, oc = 1, 3, 5
+        for i, (M, K, N) in enumerate(shapes):
+            s0 = len(segments)
+            for Ks in ((K,) if i % 3 else (K, max(1, K // 2))):
+                if variant == 0:      # row-major A (M x K), row-major B (K x N)
+                    sAm, sAk, sBk, sBn = Ks, 1, N, 1
+                elif variant == 1:    # A^T and B^T views with padded leading dimensions
+                    sAm, sAk, sBk, sBn = 1, M + 1, 1, Ks + 2
+                else:                 # padded row-major
+                    sAm, sAk, sBk, sBn = Ks + 3, 1, N + 1, 1
+                segments.append((Ks, oa, sAm, sAk, ob, sBk, sBn))
+                oa += (M - 1) * sAm + (Ks - 1) * sAk + 2
+                ob += (Ks - 1) * sBk + (N - 1) * sBn + 2
+            problems.append((M, N, oc, N + (i % 2), s0, len(segments)))
+            oc += M * (N + (i % 2)) + 1
+        problems, segments = np.array(problems, dtype=np.int64), np.array(segments, dtype=np.int64)
+        A, B = _rand(rng, oa + 4, cplx), _rand(rng, ob + 4, cplx)
+        for conj_a, conj_b in (((False, False), (True, False), (False, True)) if cplx else ((False, False),)):
+            got, info = _run_plan(problems, segments, A, B, oc, cplx, conj_a, conj_b)
+            assert info["panel_units"] > 0 and info["tiles"] > 0 and info["skinny_warps"] > 0
+            ref = exec_gemm(problems, segments, A, B, np.full(oc, np.nan, dtype=A.dtype), conj_a, conj_b)
+            live = ~np.isnan(ref.real)
+            assert np.array_equal(live, ~np.isnan(got.real))
+            for (M, N, offC, ldc, _, _) in problems:
+                blk = (offC + np.arange(M)[:, None] * ldc + np.arange(N)[None, :]).reshape(-1)
+                assert _relerr(got[blk], ref[blk]) <= TOL, (variant, M, N)
+
+
+def test_panel_products_through_dot_and_adjoint(bk):
+    """backend.dot on MPO-application shapes (plain row-major blocks) and its two adjoint GEMMs: A_b = C_b B^H is again a
+    panel product, B_b = A^H C_b a skinny reduction over 10^5..10^6 rows."""
+    rng = np.random.default_rng(37)
+    recs, oa, ob, oc = [], 0, 0, 0
+    for (M, K, N) in [(4, 4, 1_000_003), (2, 3, 250_000), (400_001, 4, 4), (1, 1, 70_000), (90_001, 2, 1)]:
+        recs.append(((oc, oc + M * N), (M, N), (oa, oa + M * K), (M, K), (ob, ob + K * N), (K, N)))
+        oa += M * K; ob += K * N; oc += M * N
+    meta = tuple(recs)
+    for cplx in (False, True):
+        A, B = _rand(rng, oa, cplx), _rand(rng, ob, cplx)
+        ref = orc.dot(A, B, meta, oc)
+        gA, gB = _dev(A).requires_grad_(True), _dev(B).requires_grad_(True)
+        out = bk.dot(gA, gB, meta, oc)
+        assert _relerr(out.detach().cpu().numpy(), ref) <= TOL
+        G = _rand(rng, oc, cplx)
+        out.backward(_dev(G))
+        ra, rb = orc.dot_backward(G, A, B, meta)
+        assert _relerr(gA.grad.cpu().numpy(), ra) <= TOL and _relerr(gB.grad.cpu().numpy(), rb) <= TOL

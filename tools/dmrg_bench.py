@@ -108,7 +108,7 @@ def gemm_roofline(backend, cplx_hint):
             e0.record()
             out = fn(Adata, Bdata, meta_dot, *rest)
             e1.record()
-            events.append((e0, e1, flops(meta_dot, Adata.is_complex() or Bdata.is_complex())))
+            events.append((e0, e1, flops(meta_dot, Adata.is_complex() or Bdata.is_complex()), meta_dot))
             return out
         return f
     for name in ("dot", "dot_unmerge"):
@@ -117,14 +117,29 @@ def gemm_roofline(backend, cplx_hint):
 
     def report():
         torch.cuda.synchronize()
-        ms = sum(a.elapsed_time(b) for a, b, _ in events)
-        fl = sum(f for _, _, f in events)
-        big = [(a.elapsed_time(b), f) for a, b, f in events if f >= 1e9]
+        ms = sum(a.elapsed_time(b) for a, b, _, _ in events)
+        fl = sum(f for _, _, f, _ in events)
+        big = [(a.elapsed_time(b), f) for a, b, f, _ in events if f >= 1e9]
+        # time by shape class: (problems, max M, max K, max N) of the call, rounded to powers of two
+        import math
+        classes = {}
+        for a, b, f, md in events:
+            if not md:
+                continue
+            lg = lambda v: 1 << max(0, math.ceil(math.log2(max(v, 1))))
+            key = (lg(len(md)), lg(max(r[3][0] for r in md)), lg(max(r[3][1] for r in md)), lg(max(r[5][1] for r in md)))
+            e = classes.setdefault(key, [0, 0.0, 0.0])
+            e[0] += 1
+            e[1] += a.elapsed_time(b)
+            e[2] += f
+        top = sorted(classes.items(), key=lambda kv: -kv[1][1])[:14]
+        by_class = [{"nprob<=": k[0], "M<=": k[1], "K<=": k[2], "N<=": k[3], "calls": v[0], "ms": round(v[1], 2), "gflop": round(v[2] * 1e-9, 1),
+                     "tflops": round(v[2] / (v[1] * 1e-3) * 1e-12, 2) if v[1] > 0 else None} for k, v in top]
         ms_big, fl_big = sum(x for x, _ in big), sum(f for _, f in big)
         return {"calls": len(events), "gflop": fl * 1e-9, "gemm_s": ms * 1e-3, "tflops": fl / (ms * 1e-3) * 1e-12 if ms > 0 else None,
                 "frac_of_37.1": fl / (ms * 1e-3) * 1e-12 / 37.1 if ms > 0 else None,
                 "calls_over_1gflop": len(big), "tflops_over_1gflop": fl_big / (ms_big * 1e-3) * 1e-12 if ms_big > 0 else None,
-                "share_of_flops_over_1gflop": fl_big / fl if fl else None}
+                "share_of_flops_over_1gflop": fl_big / fl if fl else None, "by_shape_class": by_class}
     return mod, report
 
 

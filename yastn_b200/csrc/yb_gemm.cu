@@ -486,6 +486,7 @@ struct yb_gemm_plan {
     int ws_slots = 0;       // stream-K partial-tile slots this plan needs (0: no CTA starts inside a tile)
     bool cooperative = false;
     SkinnyPlan* skinny = nullptr;   // problems with a tiny result block and a long contraction index (yb_skinny.cu)
+    PanelPlan* panel = nullptr;     // a tiny matrix times a very long one (yb_panel.cu)
 };
 
 namespace {
@@ -620,6 +621,14 @@ int create_plan(const int64_t* problems, int64_t nprob, const int64_t* segments,
         }
         for (int i : skinny_set) is_skinny[(size_t)i] = 1;
     }
+    // ... and a tiny matrix times a very long one is a streaming product (yb_panel.cu).  `is_skinny` marks both kinds: neither
+    // is tiled.
+    std::vector<int> panel_set;
+    for (int64_t i = 0; i < nprob; ++i)
+        if (!is_skinny[(size_t)i] && panel_eligible(hp[(size_t)i], hs)) {
+            panel_set.push_back((int)i);
+            is_skinny[(size_t)i] = 1;
+        }
 
     for (int64_t i = 0; i < nprob; ++i) {
         const GemmProblem& g = hp[(size_t)i];
@@ -740,10 +749,11 @@ int create_plan(const int64_t* problems, int64_t nprob, const int64_t* segments,
         (big ? nbig : nsmall) += count;
     }
 
-    for (int i : skinny_set) {
-        const GemmProblem& g = hp[(size_t)i];
-        for (int s = g.seg_begin; s < g.seg_end; ++s) macs += (int64_t)g.M * g.N * hs[(size_t)s].K;
-    }
+    for (const std::vector<int>* set : {&skinny_set, &panel_set})
+        for (int i : *set) {
+            const GemmProblem& g = hp[(size_t)i];
+            for (int s = g.seg_begin; s < g.seg_end; ++s) macs += (int64_t)g.M * g.N * hs[(size_t)s].K;
+        }
 
     yb_gemm_plan* plan = new yb_gemm_plan();
     plan->dtype = dtype;
@@ -841,6 +851,7 @@ int create_plan(const int64_t* problems, int64_t nprob, const int64_t* segments,
         plan->cooperative = coop != 0;
     }
     if (rc == kOk && !skinny_set.empty()) rc = skinny_create(hp, hs, skinny_set, cplx, device, &plan->skinny);
+    if (rc == kOk && !panel_set.empty()) rc = panel_create(hp, hs, panel_set, cplx, device, &plan->panel);
     if (rc == kOk && (plan->ws_slots > 0 || plan->skinny)) rc = workspace_reserve(device);
     cudaSetDevice(prev);
     if (rc != kOk) {
@@ -868,7 +879,7 @@ extern "C" int yb_gemm_plan_create_scatter(const int64_t* problems, int64_t npro
     return create_plan(problems, nprob, segments, nseg, scat_index, nscat, row_ptr, row_cuts, col_ptr, col_cuts, dst_ptr, dst, dtype, device, out);
 }
 
-extern "C" int yb_gemm_plan_info(const yb_gemm_plan* plan, int64_t info[8]) {
+extern "C" int yb_gemm_plan_info(const yb_gemm_plan* plan, int64_t info[10]) {
     if (!plan || !info) return fail(kErrArg, "yb_gemm_plan_info: null argument");
     info[0] = plan->ntiles;
     info[1] = plan->macs;
@@ -877,21 +888,26 @@ extern "C" int yb_gemm_plan_info(const yb_gemm_plan* plan, int64_t info[8]) {
     info[4] = plan->grid;
     info[5] = plan->nsplit;
     skinny_info(plan->skinny, &info[6], &info[7]);
+    info[8] = panel_parts(plan->panel);
+    info[9] = 0;
     return kOk;
 }
 
 extern "C" int yb_gemm_run(const yb_gemm_plan* plan, const void* A, const void* B, void* C, int flags, void* stream) {
     if (!plan) return fail(kErrArg, "yb_gemm_run: plan is null");
-    if (plan->ntiles == 0 && !plan->skinny) return kOk;
+    if (plan->ntiles == 0 && !plan->skinny && !plan->panel) return kOk;
     if (!A || !B || !C) return fail(kErrArg, "yb_gemm_run: null data pointer");
     cudaStream_t st = (cudaStream_t)stream;
     if (plan->dtype == YB_C128 && ((((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15) != 0))
         return fail(kErrArg, "yb_gemm_run: complex128 operands must be 16-byte aligned");
-    if (plan->skinny) {
+    if (plan->skinny || plan->panel) {
         ScatterTables sc = {(const ScatterInfo*)plan->scat.ptr, (const int2*)plan->rowinfo.ptr, (const int4*)plan->colinfo.ptr,
                             (const int64_t*)plan->dstpool.ptr};
-        int rc = skinny_run(plan->skinny, (const GemmProblem*)plan->problems.ptr, (const GemmSegment*)plan->segments.ptr, sc, A, B, C,
-                            flags, st);
+        int rc = kOk;
+        if (plan->skinny)
+            rc = skinny_run(plan->skinny, (const GemmProblem*)plan->problems.ptr, (const GemmSegment*)plan->segments.ptr, sc, A, B, C, flags, st);
+        if (rc == kOk && plan->panel)
+            rc = panel_run(plan->panel, (const GemmProblem*)plan->problems.ptr, (const GemmSegment*)plan->segments.ptr, sc, A, B, C, flags, st);
         if (rc != kOk) return rc;
     }
     if (plan->ntiles == 0) return kOk;
@@ -933,5 +949,6 @@ extern "C" void yb_gemm_plan_destroy(yb_gemm_plan* plan) {
     plan->colinfo.release();
     plan->dstpool.release();
     skinny_destroy(plan->skinny);
+    panel_destroy(plan->panel);
     delete plan;
 }

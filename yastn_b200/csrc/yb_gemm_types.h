@@ -57,4 +57,17 @@ int skinny_run(const SkinnyPlan* plan, const GemmProblem* problems, const GemmSe
 void skinny_destroy(SkinnyPlan* plan);
 void skinny_info(const SkinnyPlan* plan, int64_t* warps, int64_t* runs);
 
+// ---- panel path (yb_panel.cu): K <= 8 and exactly one of M, N <= 8 while the other is long ---------------------------
+constexpr int kPanelMax = 8;
+constexpr int kPanelMinStream = 256;   // shorter ones stay tiles (a second launch would cost more than the padding)
+
+struct PanelPlan;
+bool panel_eligible(const GemmProblem& P, const std::vector<GemmSegment>& hs);
+int panel_create(const std::vector<GemmProblem>& hp, const std::vector<GemmSegment>& hs, const std::vector<int>& which, bool cplx,
+                 int device, PanelPlan** out);
+int panel_run(const PanelPlan* plan, const GemmProblem* problems, const GemmSegment* segs, const ScatterTables& scat, const void* A,
+              const void* B, void* C, int flags, cudaStream_t st);
+void panel_destroy(PanelPlan* plan);
+int64_t panel_parts(const PanelPlan* plan);
+
 }  // namespace yb

@@ -766,10 +766,10 @@ class GemmPlan:
         self.device = device
 
     def info(self):
-        out = (ctypes.c_int64 * 8)()
+        out = (ctypes.c_int64 * 10)()
         _lib.check(self._lib.yb_gemm_plan_info(self.handle, out))
         return {"tiles": out[0], "macs": out[1], "big_tiles": out[2], "small_tiles": out[3], "grid": out[4], "split_ctas": out[5],
-                "skinny_warps": out[6], "skinny_runs": out[7]}
+                "skinny_warps": out[6], "skinny_runs": out[7], "panel_units": out[8]}
 
     def run(self, a_ptr, b_ptr, c_ptr, flags, stream):
         rc = self._lib.yb_gemm_run(self.handle, a_ptr, b_ptr, c_ptr, flags, stream)
