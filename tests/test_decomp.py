@@ -98,8 +98,13 @@ def test_decompositions_through_yastn_match_stock_torch(device, dtype):
     a_np = _u1_matrix(npc, dtype)
     a, r = (yastn.Tensor.from_dict(a_np.to_dict(level=2), config=c) for c in (our, ref))
     before = decomp.stats()["parallel_calls"]
-    # svd: same cuSOLVER routine per sector on both sides -> identical bits; reconstruction against the numpy input
-    U, S, V = yastn.svd(a, axes=((0, 1), (2, 3)), sU=1)
+    # svd with the reference's driver: same cuSOLVER routine per sector on both sides -> identical bits; reconstruction against
+    # the numpy input (the default driver, gesvdp for large sectors, is tested in test_gesvdp_sectors_cuda)
+    decomp.set_svd_driver("gesvd")
+    try:
+        U, S, V = yastn.svd(a, axes=((0, 1), (2, 3)), sU=1)
+    finally:
+        decomp.set_svd_driver("gesvdp")
     Ur, Sr, Vr = yastn.svd(r, axes=((0, 1), (2, 3)), sU=1)
     for x, y in ((U, Ur), (S, Sr), (V, Vr)):
         assert x.struct == y.struct and x.slices == y.slices
@@ -135,14 +140,54 @@ def test_sector_parallel_svd_many_sectors_cuda():
     shapes = [(int(m), int(n)) for m, n in zip(rng.integers(1, 200, 40), rng.integers(1, 200, 40))]
     meta, n, sizes = _svd_meta(shapes)
     fns = decomp.make(stock)
+    decomp.set_svd_driver("gesvd")
+    try:
+        for dtype in (torch.float64, torch.complex128):
+            data = torch.randn(n, dtype=dtype, device="cuda")
+            got = fns["svd"](data, meta, sizes)
+            chk = [g.clone() for g in got]            # consumer on the caller's stream
+            ref = stock.svd(data, meta, sizes)
+            for x, y in zip(chk, ref):
+                assert torch.equal(x, y)
+            assert torch.equal(fns["svdvals"](data, meta, sizes[1]), stock.svdvals(data, meta, sizes[1]))
+    finally:
+        decomp.set_svd_driver("gesvdp")
+
+
+@pytest.mark.gpu
+def test_gesvdp_sectors_cuda():
+    """Default driver: sectors of at least 48 x 48 go to cuSOLVER's polar-decomposition SVD (yastn_b200/cusolver_svdp.py).
+    Against the reference's gesvd loop on the same data: singular values within 1e-12 * S_max, identical truncation masks at
+    the DMRG tolerance, reconstruction and orthogonality to 1e-12 — tall, wide and square sectors, a spectrum graded over ten
+    decades, float64 and complex128."""
+    from yastn_b200 import cusolver_svdp
+    assert cusolver_svdp.available()
+    rng = np.random.default_rng(1)
+    shapes = [(64, 64), (200, 48), (48, 200), (163, 163), (300, 129), (5, 7), (652, 326), (50, 49), (1, 90)]
+    meta, n, sizes = _svd_meta(shapes)
+    fns = decomp.make(stock)
     for dtype in (torch.float64, torch.complex128):
         data = torch.randn(n, dtype=dtype, device="cuda")
-        got = fns["svd"](data, meta, sizes)
-        chk = [g.clone() for g in got]            # consumer on the caller's stream
-        ref = stock.svd(data, meta, sizes)
-        for x, y in zip(chk, ref):
-            assert torch.equal(x, y)
-        assert torch.equal(fns["svdvals"](data, meta, sizes[1]), stock.svdvals(data, meta, sizes[1]))
+        # give the 163 x 163 sector a graded spectrum (a DMRG two-site tensor spans ten decades)
+        sl, D = meta[3][0], meta[3][1]
+        Q1, _ = torch.linalg.qr(torch.randn(D[0], D[0], dtype=dtype, device="cuda"))
+        Q2, _ = torch.linalg.qr(torch.randn(D[1], D[1], dtype=dtype, device="cuda"))
+        sg = torch.logspace(0, -10, D[0], dtype=torch.float64, device="cuda").to(dtype)
+        data[sl[0]:sl[1]] = ((Q1 * sg) @ Q2).reshape(-1)
+        n0 = decomp.stats().get("svdp_sectors", 0)
+        U, S, Vh = fns["svd"](data, meta, sizes)
+        assert decomp.stats().get("svdp_sectors", 0) - n0 == sum(1 for m, k in shapes if min(m, k) >= 48)
+        Ur, Sr, Vr = stock.svd(data, meta, sizes)
+        for (slA, DA, slU, DU, slS, slV, DV) in meta:
+            s, sr = S[slS[0]:slS[1]], Sr[slS[0]:slS[1]]
+            assert float((s - sr).abs().max()) <= 1e-12 * float(sr.max())
+            assert torch.equal(s > 1e-10 * s.max(), sr > 1e-10 * sr.max())          # same truncation mask
+            u, vh = U[slU[0]:slU[1]].view(DU), Vh[slV[0]:slV[1]].view(DV)
+            A = data[slA[0]:slA[1]].view(DA)
+            assert float(torch.linalg.norm(u * s.to(dtype) @ vh - A)) <= 1e-12 * float(torch.linalg.norm(A))
+            k = s.numel()
+            eye = torch.eye(k, dtype=dtype, device="cuda")
+            assert float(torch.linalg.norm(u.conj().t() @ u - eye)) <= 1e-11 and float(torch.linalg.norm(vh @ vh.conj().t() - eye)) <= 1e-11
 
 
 def test_activate_rebinds_and_deactivate_restores_every_function():
