@@ -346,17 +346,27 @@ def main():
     work = []   # per contraction: sharded stage metas, device operands, flops
     total_flops = 0
     gen = torch.Generator(device=dev).manual_seed(1234)
+
+    def rnd(n):
+        x = torch.rand(n, dtype=torch.float64, device=dev, generator=gen) * 2 - 1
+        if cplx:
+            x = torch.complex(x, torch.rand(n, dtype=torch.float64, device=dev, generator=gen) * 2 - 1)
+        return x
+    # the three contractions of one size share their operands, as in the reference arm: P1 = A.F, P2 = A.B4, P3 = A^T.B4
+    # (the transpose is lazy: same storage)
+    operands = {}
     for name, case in cases:
+        size_tag, pat = name.rsplit("_", 1)
+        akey, bkey = (size_tag, "A"), (size_tag, "F" if pat == "P1" else "B4")
+        for key, n in ((akey, case["a"]["size"]), (bkey, case["b"]["size"])):
+            if key not in operands:
+                operands[key] = rnd(n)
+            assert operands[key].numel() == n
         stage = case["f2m"]
         total_flops += case_flops(stage, cplx)
         if world > 1:
             stage, _ = sharding.shard_f2m(stage, rank, world)
-        def rnd(n):
-            x = torch.rand(n, dtype=torch.float64, device=dev, generator=gen) * 2 - 1
-            if cplx:
-                x = torch.complex(x, torch.rand(n, dtype=torch.float64, device=dev, generator=gen) * 2 - 1)
-            return x
-        work.append({"name": name, "stage": stage, "A": rnd(case["a"]["size"]), "B": rnd(case["b"]["size"]),
+        work.append({"name": name, "stage": stage, "A": operands[akey], "B": operands[bkey], "akey": akey, "bkey": bkey,
                      "flops": case_flops(stage, cplx)})
 
     launches = [0]
@@ -446,53 +456,71 @@ def main():
     own_flops = sum(w["flops"] for w in work)
     tile_flops = sum(w["flops"] for w, sk in zip(work, skinny) if not sk)
 
-    # end-to-end: host operands (pinned) -> H2D -> 4 backend calls -> D2H of the result
+    # end-to-end: host operands (pinned) -> H2D -> backend calls -> D2H of every result, every step.  The three contractions of
+    # one size share their operands, so a step uploads each of A, F, B4 once per size (what a user of the API does as well)
     e2e = None
     if not args.no_e2e:
-        host = [(w["A"].cpu().pin_memory(), w["B"].cpu().pin_memory()) for w in work]
+        host_ops = {k: v.cpu().pin_memory() for k, v in operands.items()}
         out_host = [torch.empty(w["stage"]["dot"]["Dsize"], dtype=tdt).pin_memory() for w in work]
         # N > 1: a rank moves only the operand blocks its sectors read and the result blocks it produces (coalesced ranges of
         # the 1-D storage); N = 1: the whole tensors
         ranges = [shard_ranges(w["stage"]) if world > 1 else None for w in work]
         isz_ = 16 if cplx else 8
+        groups = {}          # size tag -> contractions of that size
+        for i, w in enumerate(work):
+            groups.setdefault(w["akey"][0], []).append(i)
+        need = {}            # operand -> ranges to upload (None: everything)
+        for i, w in enumerate(work):
+            for key, which in ((w["akey"], 0), (w["bkey"], 1)):
+                if ranges[i] is None:
+                    need[key] = None
+                else:
+                    need[key] = _coalesce(list(need.get(key) or []) + list(ranges[i][which]))
         if world > 1:
-            h2d = sum(isz_ * sum(hi - lo for lo, hi in r[0] + r[1]) for r in ranges)
+            h2d = sum(isz_ * sum(hi - lo for lo, hi in r) for r in need.values())
             d2h = sum(isz_ * sum(hi - lo for lo, hi in r[2]) for r in ranges)
         else:
-            h2d = sum(a.numel() * a.element_size() + b.numel() * b.element_size() for a, b in host)
+            h2d = sum(v.numel() * v.element_size() for v in host_ops.values())
             d2h = sum(o.numel() * o.element_size() for o in out_host)
         e2e_steps = max(1, min(args.steps, 5))
-        # three streams: H2D of the next contraction and D2H of the previous one overlap the kernels of the current one
-        # (PCIe is full duplex); every contraction still does H2D -> merge/merge/GEMM+unmerge -> D2H inside the timed region
+        # three streams: H2D of the next size and D2H of the previous results overlap the kernels of the current size
+        # (PCIe is full duplex); every step still does H2D -> merge/merge/GEMM+unmerge -> D2H inside the timed region
         s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        # largest size first: its D2H (2 GB at D=16384) then overlaps the H2D and kernels of the others; consecutive
+        # steps are not joined (the copy streams are ordered by events only), the timed region ends when the last D2H lands
+        group_order = sorted(groups, key=lambda g: -max(out_host[i].numel() for i in groups[g]))
+
         def e2e_pass():
             cur = torch.cuda.current_stream(dev)
-            for w, (ha, hb), ho, rg in e2e_order:
+            for gname in group_order:
+                devops = {}
                 with torch.cuda.stream(s_in):
-                    if rg is None:
-                        A = ha.to(dev, non_blocking=True); B = hb.to(dev, non_blocking=True)
-                    else:
-                        A = torch.empty(ha.numel(), dtype=tdt, device=dev); B = torch.empty(hb.numel(), dtype=tdt, device=dev)
-                        for lo, hi in rg[0]:
-                            A[lo:hi].copy_(ha[lo:hi], non_blocking=True)
-                        for lo, hi in rg[1]:
-                            B[lo:hi].copy_(hb[lo:hi], non_blocking=True)
+                    for key in sorted({k for i in groups[gname] for k in (work[i]["akey"], work[i]["bkey"])}):
+                        h = host_ops[key]
+                        if need[key] is None:
+                            devops[key] = h.to(dev, non_blocking=True)
+                        else:
+                            t = torch.empty(h.numel(), dtype=tdt, device=dev)
+                            for lo, hi in need[key]:
+                                t[lo:hi].copy_(h[lo:hi], non_blocking=True)
+                            devops[key] = t
                     ready = torch.cuda.Event(); ready.record(s_in)
                 cur.wait_event(ready)
-                A.record_stream(cur); B.record_stream(cur)
-                C = contract(w, A, B)
-                done = torch.cuda.Event(); done.record(cur)
-                s_out.wait_event(done)
-                with torch.cuda.stream(s_out):
-                    if rg is None:
-                        ho.copy_(C, non_blocking=True)
-                    else:
-                        for lo, hi in rg[2]:
-                            ho[lo:hi].copy_(C[lo:hi], non_blocking=True)
-                C.record_stream(s_out)
-        # largest contraction first: its D2H (2 GB at D=16384) then overlaps the H2D and kernels of the others; consecutive
-        # steps are not joined (the copy streams are ordered by events only), the timed region ends when the last D2H lands
-        e2e_order = sorted(zip(work, host, out_host, ranges), key=lambda t: -t[2].numel())
+                for t in devops.values():
+                    t.record_stream(cur)
+                for i in sorted(groups[gname], key=lambda i: -out_host[i].numel()):
+                    w, ho, rg = work[i], out_host[i], ranges[i]
+                    C = contract(w, devops[w["akey"]], devops[w["bkey"]])
+                    done = torch.cuda.Event(); done.record(cur)
+                    s_out.wait_event(done)
+                    with torch.cuda.stream(s_out):
+                        if rg is None:
+                            ho.copy_(C, non_blocking=True)
+                        else:
+                            for lo, hi in rg[2]:
+                                ho[lo:hi].copy_(C[lo:hi], non_blocking=True)
+                    C.record_stream(s_out)
+
         def e2e_join():
             cur = torch.cuda.current_stream(dev)
             cur.wait_stream(s_in)
@@ -563,7 +591,7 @@ def main():
         if e2e is not None:
             line["e2e"] = e2e
         if world == 1:
-            del work
+            del work, operands
             torch.cuda.empty_cache()
             if not args.no_cpu_baseline:
                 line["cpu_baseline"] = cpu_baseline(cplx, args.sizes)

@@ -220,6 +220,7 @@ template <bool CPLX, int AL, int BL, int BM, int BN>
 struct TileKernel {
     using TR = ElemTraits<CPLX>;
     static constexpr int ES = TR::ES, BK = TR::BK, KSTEPS = TR::KSTEPS;
+    static constexpr int BM_ = BM, BN_ = BN;
     static constexpr int WM = BM / 2, WN = BN / 2;     // warp tile
     static constexpr int MT = WM / 8, NT = WN / 8;     // 8x8 DMMA tiles per warp
     static constexpr int NACC = MT * NT * (CPLX ? 4 : 2);
@@ -473,6 +474,329 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_kernel(const GemmArgs g)
     }
 }
 
+// =====================================================================================================================
+// Warp-specialised variant: a producer warpgroup streams operand tiles through the shared-memory ring, a consumer warpgroup
+// (the same 2 x 2 warps and fragment layout as gemm_kernel) issues the DMMAs.
+//
+// Why (ncu on gemm_kernel, profiles/ncu_r02_gemm_u1u1.txt): every k-iteration the math warps also issue 12 cp.async each
+// with their address arithmetic and meet at a CTA barrier; a tile shorter than ~16 k-iterations (K <= 163 in U1xU1 sectors)
+// pays the full pipeline fill and the epilogue with an idle tensor pipe (DMMA 71 % busy while active, 64 % of the launch),
+// and at 254 registers the kernel has no room to skip the padded 8 x 8 slices of edge tiles.  Here
+//   * the loaders live in the producer warps only (setmaxnreg moves their registers to the consumers: 40 / 216 per thread at
+//     256 threads and 2 CTAs per SM),
+//   * stages are handed over through mbarriers (full: cp.async.mbarrier.arrive of the 128 producer threads; empty: one arrive
+//     per consumer warp), so there is no CTA-wide barrier in the main loop and consumer warps drift up to a ring apart,
+//   * the producer runs ahead ACROSS tile boundaries: the first stages of the next tile are in flight while the consumers
+//     finish the current tile and write its epilogue.
+// =====================================================================================================================
+constexpr int kWsThreads = 256;          // warpgroup 0: consumers (math), warpgroup 1: producers (loads)
+constexpr int kWsProducerRegs = 40;
+constexpr int kWsConsumerRegs = 216;
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cp_async(uint32_t bar) {   // arrives once all cp.async of this thread have landed
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, 128;\n" ::: "memory"); }
+
+template <bool CPLX, int AL, int BL>
+struct WsShape {
+    using G = GroupKernel<CPLX, AL, BL>;
+    static constexpr int STAGE_BYTES = G::Big::STAGE_BYTES > G::Small::STAGE_BYTES ? G::Big::STAGE_BYTES : G::Small::STAGE_BYTES;
+    static constexpr int BAR_BYTES = 2 * kStages * 8;
+    static constexpr int SMEM_BYTES = STAGE_BYTES * kStages + BAR_BYTES;
+};
+
+// iterations [ib, ie) of tile T that actually exist
+__device__ __forceinline__ int ws_tile_iters(const GemmTile& T, int ib, int ie) {
+    const int n = min(ie, T.iters) - ib;
+    return n > 0 ? n : 0;
+}
+
+// ---- producer: all 128 threads of warpgroup 1 -------------------------------------------------------------------------
+template <bool CPLX, int AL, int BL, int BM, int BN>
+__device__ __forceinline__ void ws_produce_tile(const GemmArgs& g, const GemmProblem& P, const GemmTile& T, int it_begin, int n_iters,
+                                                uint32_t smem, uint32_t bars, int stage_bytes, uint32_t& it_glob, int tid) {
+    using TR = ElemTraits<CPLX>;
+    constexpr int ES = TR::ES, BK = TR::BK;
+    constexpr int A_BYTES = BM * kRowBytes;
+    const GemmSegment* __restrict__ segs = g.segs;
+    const bool base_aligned = g.base_aligned != 0;
+    TileLoader<CPLX, AL, BM> la;
+    TileLoader<CPLX, BL, BN> lb;
+    int ld_seg = P.seg_begin, ld_k0 = 0, ld_K = 0;
+    {   // locate iteration it_begin
+        int skip = it_begin;
+        for (;; ++ld_seg) {
+            const int K = segs[ld_seg].K;
+            const int n = (K + BK - 1) / BK;
+            if (skip < n) {
+                ld_k0 = skip * BK;
+                ld_K = K;
+                break;
+            }
+            skip -= n;
+        }
+    }
+    bool fresh = true;
+    for (int it = 0; it < n_iters; ++it) {
+        if (ld_k0 >= ld_K) {   // next segment with K > 0
+            do {
+                ++ld_seg;
+                ld_K = segs[ld_seg].K;
+            } while (ld_K <= 0);
+            ld_k0 = 0;
+            fresh = true;
+        }
+        if (fresh) {
+            const GemmSegment& S = segs[ld_seg];
+            la.init(g.A + S.offA * ES, S.sAm, S.sAk, P.M, T.m0, ld_k0, base_aligned && (S.align & 1), tid);
+            lb.init(g.B + S.offB * ES, S.sBn, S.sBk, P.N, T.n0, ld_k0, base_aligned && (S.align & 2), tid);
+            fresh = false;
+        }
+        const uint32_t stage = it_glob % kStages, phase = (it_glob / kStages) & 1;
+        mbar_wait(bars + (kStages + stage) * 8, phase ^ 1);            // the consumers have released this stage
+        const uint32_t sa = smem + stage * stage_bytes, sb = sa + A_BYTES;
+        la.issue(sa, ld_K - ld_k0);
+        lb.issue(sb, ld_K - ld_k0);
+        mbar_arrive_cp_async(bars + stage * 8);
+        ld_k0 += BK;
+        ++it_glob;
+    }
+}
+
+// ---- consumer: warpgroup 0, the 2 x 2 warp layout of TileKernel -------------------------------------------------------
+template <bool CPLX, int AL, int BL, int BM, int BN>
+__device__ __forceinline__ void ws_consume_tile(const GemmArgs& g, const GemmProblem& P, const GemmTile& T, int tile_index, int it_begin,
+                                                int it_end, int n_iters, uint32_t smem, uint32_t bars, int stage_bytes, uint32_t& it_glob) {
+    using TR = ElemTraits<CPLX>;
+    constexpr int ES = TR::ES, KSTEPS = TR::KSTEPS;
+    constexpr int WM = BM / 2, WN = BN / 2, MT = WM / 8, NT = WN / 8;
+    constexpr int A_BYTES = BM * kRowBytes;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm0 = (warp >> 1) * WM, wn0 = (warp & 1) * WN;
+    const int lx = lane >> 2, lk = lane & 3;
+    const bool base_aligned = g.base_aligned != 0;
+
+    double acc[MT][NT][CPLX ? 4 : 2];
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+            for (int c = 0; c < (CPLX ? 4 : 2); ++c) acc[i][j][c] = 0.0;
+
+    const uint32_t sgnA = (CPLX && (g.flags & YB_GEMM_CONJ_A)) ? 0x80000000u : 0u;
+    const uint32_t sgnB = (CPLX && (g.flags & YB_GEMM_CONJ_B)) ? 0x80000000u : 0u;
+    uint32_t aoff[MT], boff[NT];
+#pragma unroll
+    for (int i = 0; i < MT; ++i) aoff[i] = frag_offset<CPLX, AL, BM>(wm0 + i * 8 + lx, lk);
+#pragma unroll
+    for (int j = 0; j < NT; ++j) boff[j] = A_BYTES + frag_offset<CPLX, BL, BN>(wn0 + j * 8 + lx, lk);
+
+    for (int it = 0; it < n_iters; ++it) {
+        const uint32_t stage = it_glob % kStages, phase = (it_glob / kStages) & 1;
+        mbar_wait(bars + stage * 8, phase);                              // the stage has landed
+        const uint32_t sa = smem + stage * stage_bytes;
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+            if constexpr (!CPLX) {
+                double af[MT], bf[NT];
+#pragma unroll
+                for (int i = 0; i < MT; ++i) af[i] = lds64(sa + (AL == KC ? (aoff[i] ^ (ks * 32)) : (aoff[i] + ks * 4 * BM * ES)));
+#pragma unroll
+                for (int j = 0; j < NT; ++j) bf[j] = lds64(sa + (BL == KC ? (boff[j] ^ (ks * 32)) : (boff[j] + ks * 4 * BN * ES)));
+#pragma unroll
+                for (int i = 0; i < MT; ++i)
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            } else {
+                double2 af[MT], bf[NT];
+                double naf[MT];
+#pragma unroll
+                for (int i = 0; i < MT; ++i) {
+                    af[i] = lds128(sa + (AL == KC ? (aoff[i] ^ (ks * 64)) : (aoff[i] + ks * 4 * BM * ES)));
+                    af[i].y = flip_sign(af[i].y, sgnA);
+                    naf[i] = flip_sign(af[i].y, 0x80000000u);
+                }
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    bf[j] = lds128(sa + (BL == KC ? (boff[j] ^ (ks * 64)) : (boff[j] + ks * 4 * BN * ES)));
+                    bf[j].y = flip_sign(bf[j].y, sgnB);
+                }
+#pragma unroll
+                for (int i = 0; i < MT; ++i)
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) {
+                        dmma(acc[i][j][0], acc[i][j][1], af[i].x, bf[j].x);
+                        dmma(acc[i][j][0], acc[i][j][1], naf[i], bf[j].y);
+                        dmma(acc[i][j][2], acc[i][j][3], af[i].x, bf[j].y);
+                        dmma(acc[i][j][2], acc[i][j][3], af[i].y, bf[j].x);
+                    }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + (kStages + stage) * 8);        // this warp is done reading the stage
+        ++it_glob;
+    }
+
+    // ---- stream-K fix-up (consumer threads only; same protocol as gemm_kernel) -------------------------------------------
+    const bool starts = it_begin == 0, ends = it_end >= T.iters;
+    if (!starts) {
+        double* slot = g.ws + (size_t)blockIdx.x * kWsDoubles + tid;
+        int r = 0;
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+#pragma unroll
+                for (int c = 0; c < (CPLX ? 4 : 2); ++c) __stcg(slot + (r++) * kGemmThreads, acc[i][j][c]);
+        __threadfence();
+        consumer_bar_sync();
+        if (tid == 0) st_release(g.sync_flags + blockIdx.x, 1);
+        return;
+    }
+    if (!ends) {
+        for (int d = blockIdx.x + 1;; ++d) {
+            const CtaRange Rd = g.ranges[d];
+            if (tid == 0) {
+                while (ld_acquire(g.sync_flags + d) == 0) __nanosleep(64);
+                g.sync_flags[d] = 0;
+            }
+            consumer_bar_sync();
+            const double* slot = g.ws + (size_t)d * kWsDoubles + tid;
+            int r = 0;
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+#pragma unroll
+                for (int j = 0; j < NT; ++j)
+#pragma unroll
+                    for (int c = 0; c < (CPLX ? 4 : 2); ++c) acc[i][j][c] += __ldcg(slot + (r++) * kGemmThreads);
+            if (Rd.tile_end > tile_index || Rd.it_end >= T.iters) break;
+        }
+    }
+
+    // ---- epilogue ---------------------------------------------------------------------------------------------------------
+    using T2 = typename std::conditional<CPLX, double2, double>::type;
+    auto value = [&](int i, int j, int e) -> T2 {
+        if constexpr (CPLX) return make_double2(acc[i][j][e], acc[i][j][2 + e]);
+        else return acc[i][j][e];
+    };
+    if (P.scat < 0) {
+        T2* Cp = reinterpret_cast<T2*>(g.C) + P.offC;
+        const bool vec = !CPLX && base_aligned && ((P.offC & 1) == 0) && ((P.ldc & 1) == 0);
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+            const int row = T.m0 + wm0 + i * 8 + lx;
+            if (row < P.M) {
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    const int col = T.n0 + wn0 + j * 8 + 2 * lk;
+                    T2* p = Cp + (int64_t)row * P.ldc + col;
+                    if constexpr (!CPLX) {
+                        if (vec && col + 1 < P.N) {
+                            *reinterpret_cast<double2*>(p) = make_double2(acc[i][j][0], acc[i][j][1]);
+                            continue;
+                        }
+                    }
+                    if (col < P.N) p[0] = value(i, j, 0);
+                    if (col + 1 < P.N) p[1] = value(i, j, 1);
+                }
+            }
+        }
+    } else {
+        const ScatterInfo S = g.scat[P.scat];
+        T2* out = reinterpret_cast<T2*>(g.C);
+        int2 ri[MT];
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+            const int row = T.m0 + wm0 + i * 8 + lx;
+            ri[i] = row < P.M ? g.rowinfo[S.row_off + row] : make_int2(-1, 0);
+        }
+        const int64_t* dst = g.dstpool + S.dst_off;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const int col = T.n0 + wn0 + j * 8 + 2 * lk;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                if (col + e < P.N) {
+                    const int4 ci = g.colinfo[S.col_off + col + e];
+#pragma unroll
+                    for (int i = 0; i < MT; ++i)
+                        if (ri[i].x >= 0) out[dst[(int64_t)ri[i].x * S.ncs + ci.x] + (int64_t)ri[i].y * ci.z + ci.y] = value(i, j, e);
+                }
+            }
+        }
+    }
+}
+
+template <bool CPLX, int AL, int BL>
+__global__ void __launch_bounds__(kWsThreads, 2) gemm_ws_kernel(const GemmArgs g) {
+    extern __shared__ __align__(128) char smem_raw[];
+    using W = WsShape<CPLX, AL, BL>;
+    using G = GroupKernel<CPLX, AL, BL>;
+    const uint32_t smem = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t bars = smem + W::STAGE_BYTES * kStages;      // full[0..kStages), empty[0..kStages)
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(bars + s * 8, kGemmThreads);               // one cp.async arrive per producer thread
+            mbar_init(bars + (kStages + s) * 8, kGemmThreads / 32);   // one arrive per consumer warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    const CtaRange R = g.ranges[blockIdx.x];
+    uint32_t it_glob = 0;
+    if (tid >= kGemmThreads) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(kWsProducerRegs));
+        const int ptid = tid - kGemmThreads;
+        for (int t = R.tile_begin; t <= R.tile_end; ++t) {
+            const GemmTile T = g.tiles[t];
+            const GemmProblem P = g.problems[T.prob];
+            const int ib = (t == R.tile_begin) ? R.it_begin : 0;
+            const int ie = (t == R.tile_end) ? R.it_end : max(T.iters, 1);
+            const int n = ws_tile_iters(T, ib, ie);
+            if (n == 0) continue;
+            if (T.cfg == 0)
+                ws_produce_tile<CPLX, AL, BL, G::Big::BM_, G::Big::BN_>(g, P, T, ib, n, smem, bars, W::STAGE_BYTES, it_glob, ptid);
+            else
+                ws_produce_tile<CPLX, AL, BL, G::Small::BM_, G::Small::BN_>(g, P, T, ib, n, smem, bars, W::STAGE_BYTES, it_glob, ptid);
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(kWsConsumerRegs));
+        for (int t = R.tile_begin; t <= R.tile_end; ++t) {
+            const GemmTile T = g.tiles[t];
+            const GemmProblem P = g.problems[T.prob];
+            const int ib = (t == R.tile_begin) ? R.it_begin : 0;
+            const int ie = (t == R.tile_end) ? R.it_end : max(T.iters, 1);
+            const int n = ws_tile_iters(T, ib, ie);
+            if (T.cfg == 0)
+                ws_consume_tile<CPLX, AL, BL, G::Big::BM_, G::Big::BN_>(g, P, T, t, ib, ie, n, smem, bars, W::STAGE_BYTES, it_glob);
+            else
+                ws_consume_tile<CPLX, AL, BL, G::Small::BM_, G::Small::BN_>(g, P, T, t, ib, ie, n, smem, bars, W::STAGE_BYTES, it_glob);
+        }
+    }
+}
+
 }  // namespace yb
 
 using namespace yb;
@@ -491,16 +815,31 @@ struct yb_gemm_plan {
 
 namespace {
 
+// Kernel variant: the warp-specialised kernel unless YB_GEMM_CLASSIC=1 is set in the environment (A/B measurements).
+bool use_ws_kernel() {
+    static const bool ws = [] {
+        const char* e = getenv("YB_GEMM_CLASSIC");
+        return !(e && e[0] == '1');
+    }();
+    return ws;
+}
+
 template <bool CPLX, int AL, int BL>
 int occupancy(int device, int* blocks_per_sm) {
     using G = GroupKernel<CPLX, AL, BL>;
+    using W = WsShape<CPLX, AL, BL>;
     static int cached[64] = {0};   // per device: the attribute has to be set once per context, the answer never changes
     if (device >= 0 && device < 64 && cached[device] > 0) {
         *blocks_per_sm = cached[device];
         return kOk;
     }
-    YB_CUDA(cudaFuncSetAttribute(gemm_kernel<CPLX, AL, BL>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
-    YB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, gemm_kernel<CPLX, AL, BL>, kGemmThreads, G::SMEM_BYTES));
+    if (use_ws_kernel()) {
+        YB_CUDA(cudaFuncSetAttribute(gemm_ws_kernel<CPLX, AL, BL>, cudaFuncAttributeMaxDynamicSharedMemorySize, W::SMEM_BYTES));
+        YB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, gemm_ws_kernel<CPLX, AL, BL>, kWsThreads, W::SMEM_BYTES));
+    } else {
+        YB_CUDA(cudaFuncSetAttribute(gemm_kernel<CPLX, AL, BL>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
+        YB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, gemm_kernel<CPLX, AL, BL>, kGemmThreads, G::SMEM_BYTES));
+    }
     if (device >= 0 && device < 64) cached[device] = *blocks_per_sm;
     return kOk;
 }
@@ -516,12 +855,18 @@ int occupancy_layout(int al, int bl, int device, int* b) {
 template <bool CPLX, int AL, int BL>
 int launch(const yb_gemm_plan* p, const GemmArgs& args, cudaStream_t st) {
     using G = GroupKernel<CPLX, AL, BL>;
+    using W = WsShape<CPLX, AL, BL>;
+    const bool ws = use_ws_kernel();
+    const void* fn = ws ? (const void*)gemm_ws_kernel<CPLX, AL, BL> : (const void*)gemm_kernel<CPLX, AL, BL>;
+    const int threads = ws ? kWsThreads : kGemmThreads;
+    const size_t smem = ws ? (size_t)W::SMEM_BYTES : (size_t)G::SMEM_BYTES;
     if (p->cooperative) {
         // CTAs that finish a split tile wait for the partials of other CTAs: a cooperative launch makes the driver
         // guarantee that the whole grid (<= SMs x occupancy) is resident at once, whatever else runs on the device
         void* kargs[] = {(void*)&args};
-        YB_CUDA(cudaLaunchCooperativeKernel((const void*)gemm_kernel<CPLX, AL, BL>, dim3(p->grid), dim3(kGemmThreads), kargs,
-                                            (size_t)G::SMEM_BYTES, st));
+        YB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(p->grid), dim3(threads), kargs, smem, st));
+    } else if (ws) {
+        gemm_ws_kernel<CPLX, AL, BL><<<p->grid, kWsThreads, W::SMEM_BYTES, st>>>(args);
     } else {
         gemm_kernel<CPLX, AL, BL><<<p->grid, kGemmThreads, G::SMEM_BYTES, st>>>(args);
     }
