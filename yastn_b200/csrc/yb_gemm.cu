@@ -490,6 +490,7 @@ __global__ void __launch_bounds__(kGemmThreads, 2) gemm_kernel(const GemmArgs g)
 //     finish the current tile and write its epilogue.
 // =====================================================================================================================
 constexpr int kWsThreads = 256;          // warpgroup 0: consumers (math), warpgroup 1: producers (loads)
+constexpr int kFlagNoEdgeSkip = 0x100;   // internal run flag (YB_GEMM_NOSKIP=1): multiply the padding of edge tiles too (A/B measurements)
 constexpr int kWsProducerRegs = 40;
 constexpr int kWsConsumerRegs = 216;
 
@@ -583,7 +584,11 @@ __device__ __forceinline__ void ws_produce_tile(const GemmArgs& g, const GemmPro
 }
 
 // ---- consumer: warpgroup 0, the 2 x 2 warp layout of TileKernel -------------------------------------------------------
-template <bool CPLX, int AL, int BL, int BM, int BN>
+// EDGE: the tile sticks out of the problem; every warp multiplies only the 8-row / 8-column slices of its 32 x 64 (16 x 16 ...)
+// warp tile that hold at least one valid row / column.  A sector of 68 rows is one full row of tiles plus one whose lower
+// warps have nothing to do and whose upper warps use one slice of four: without the guards 47 % of its DMMAs are padding.
+// Full tiles run the unguarded instantiation.
+template <bool CPLX, int AL, int BL, int BM, int BN, bool EDGE>
 __device__ __forceinline__ void ws_consume_tile(const GemmArgs& g, const GemmProblem& P, const GemmTile& T, int tile_index, int it_begin,
                                                 int it_end, int n_iters, uint32_t smem, uint32_t bars, int stage_bytes, uint32_t& it_glob) {
     using TR = ElemTraits<CPLX>;
@@ -610,6 +615,13 @@ __device__ __forceinline__ void ws_consume_tile(const GemmArgs& g, const GemmPro
     for (int i = 0; i < MT; ++i) aoff[i] = frag_offset<CPLX, AL, BM>(wm0 + i * 8 + lx, lk);
 #pragma unroll
     for (int j = 0; j < NT; ++j) boff[j] = A_BYTES + frag_offset<CPLX, BL, BN>(wn0 + j * 8 + lx, lk);
+    // slices of this warp's tile that hold valid rows / columns (warp-uniform)
+    int mt_valid = MT, nt_valid = NT;
+    if constexpr (EDGE) {
+        mt_valid = min(MT, max(0, (P.M - T.m0 - wm0 + 7) >> 3));
+        nt_valid = min(NT, max(0, (P.N - T.n0 - wn0 + 7) >> 3));
+        if (mt_valid == 0 || nt_valid == 0) mt_valid = nt_valid = 0;
+    }
 
     for (int it = 0; it < n_iters; ++it) {
         const uint32_t stage = it_glob % kStages, phase = (it_glob / kStages) & 1;
@@ -617,7 +629,46 @@ __device__ __forceinline__ void ws_consume_tile(const GemmArgs& g, const GemmPro
         const uint32_t sa = smem + stage * stage_bytes;
 #pragma unroll
         for (int ks = 0; ks < KSTEPS; ++ks) {
-            if constexpr (!CPLX) {
+            if constexpr (EDGE) {
+                if constexpr (!CPLX) {
+                    double bf[NT];
+#pragma unroll
+                    for (int j = 0; j < NT; ++j)
+                        bf[j] = j < nt_valid ? lds64(sa + (BL == KC ? (boff[j] ^ (ks * 32)) : (boff[j] + ks * 4 * BN * ES))) : 0.0;
+#pragma unroll
+                    for (int i = 0; i < MT; ++i) {
+                        if (i < mt_valid) {
+                            const double af = lds64(sa + (AL == KC ? (aoff[i] ^ (ks * 32)) : (aoff[i] + ks * 4 * BM * ES)));
+#pragma unroll
+                            for (int j = 0; j < NT; ++j)
+                                if (j < nt_valid) dmma(acc[i][j][0], acc[i][j][1], af, bf[j]);
+                        }
+                    }
+                } else {
+                    double2 bf[NT];
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) {
+                        bf[j] = j < nt_valid ? lds128(sa + (BL == KC ? (boff[j] ^ (ks * 64)) : (boff[j] + ks * 4 * BN * ES))) : make_double2(0.0, 0.0);
+                        bf[j].y = flip_sign(bf[j].y, sgnB);
+                    }
+#pragma unroll
+                    for (int i = 0; i < MT; ++i) {
+                        if (i < mt_valid) {
+                            double2 af = lds128(sa + (AL == KC ? (aoff[i] ^ (ks * 64)) : (aoff[i] + ks * 4 * BM * ES)));
+                            af.y = flip_sign(af.y, sgnA);
+                            const double naf = flip_sign(af.y, 0x80000000u);
+#pragma unroll
+                            for (int j = 0; j < NT; ++j)
+                                if (j < nt_valid) {
+                                    dmma(acc[i][j][0], acc[i][j][1], af.x, bf[j].x);
+                                    dmma(acc[i][j][0], acc[i][j][1], naf, bf[j].y);
+                                    dmma(acc[i][j][2], acc[i][j][3], af.x, bf[j].y);
+                                    dmma(acc[i][j][2], acc[i][j][3], af.y, bf[j].x);
+                                }
+                        }
+                    }
+                }
+            } else if constexpr (!CPLX) {
                 double af[MT], bf[NT];
 #pragma unroll
                 for (int i = 0; i < MT; ++i) af[i] = lds64(sa + (AL == KC ? (aoff[i] ^ (ks * 32)) : (aoff[i] + ks * 4 * BM * ES)));
@@ -789,10 +840,15 @@ __global__ void __launch_bounds__(kWsThreads, 2) gemm_ws_kernel(const GemmArgs g
             const int ib = (t == R.tile_begin) ? R.it_begin : 0;
             const int ie = (t == R.tile_end) ? R.it_end : max(T.iters, 1);
             const int n = ws_tile_iters(T, ib, ie);
-            if (T.cfg == 0)
-                ws_consume_tile<CPLX, AL, BL, G::Big::BM_, G::Big::BN_>(g, P, T, t, ib, ie, n, smem, bars, W::STAGE_BYTES, it_glob);
-            else
-                ws_consume_tile<CPLX, AL, BL, G::Small::BM_, G::Small::BN_>(g, P, T, t, ib, ie, n, smem, bars, W::STAGE_BYTES, it_glob);
+            const int bm = T.cfg == 0 ? G::Big::BM_ : G::Small::BM_, bn = T.cfg == 0 ? G::Big::BN_ : G::Small::BN_;
+            const bool edge = (T.m0 + bm > P.M || T.n0 + bn > P.N) && !(g.flags & kFlagNoEdgeSkip);
+            if (T.cfg == 0) {
+                if (edge) ws_consume_tile<CPLX, AL, BL, G::Big::BM_, G::Big::BN_, true>(g, P, T, t, ib, ie, n, smem, bars, W::STAGE_BYTES, it_glob);
+                else ws_consume_tile<CPLX, AL, BL, G::Big::BM_, G::Big::BN_, false>(g, P, T, t, ib, ie, n, smem, bars, W::STAGE_BYTES, it_glob);
+            } else {
+                if (edge) ws_consume_tile<CPLX, AL, BL, G::Small::BM_, G::Small::BN_, true>(g, P, T, t, ib, ie, n, smem, bars, W::STAGE_BYTES, it_glob);
+                else ws_consume_tile<CPLX, AL, BL, G::Small::BM_, G::Small::BN_, false>(g, P, T, t, ib, ie, n, smem, bars, W::STAGE_BYTES, it_glob);
+            }
         }
     }
 }
@@ -1277,7 +1333,8 @@ extern "C" int yb_gemm_run(const yb_gemm_plan* plan, const void* A, const void* 
     args.A = (const char*)A;
     args.B = (const char*)B;
     args.C = (char*)C;
-    args.flags = flags;
+    static const bool no_skip = [] { const char* e = getenv("YB_GEMM_NOSKIP"); return e && e[0] == '1'; }();
+    args.flags = (flags & 0xff) | (no_skip ? kFlagNoEdgeSkip : 0);
     args.base_aligned = (((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15) == 0;
     if (plan->dtype == YB_C128) return dispatch_layout<true>(plan, args, st);
     return dispatch_layout<false>(plan, args, st);
