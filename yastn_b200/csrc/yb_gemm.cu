@@ -584,10 +584,10 @@ __device__ __forceinline__ void ws_produce_tile(const GemmArgs& g, const GemmPro
 }
 
 // ---- consumer: warpgroup 0, the 2 x 2 warp layout of TileKernel -------------------------------------------------------
-// EDGE: the tile sticks out of the problem; every warp multiplies only the 8-row / 8-column slices of its 32 x 64 (16 x 16 ...)
-// warp tile that hold at least one valid row / column.  A sector of 68 rows is one full row of tiles plus one whose lower
-// warps have nothing to do and whose upper warps use one slice of four: without the guards 47 % of its DMMAs are padding.
-// Full tiles run the unguarded instantiation.
+// EDGE: the tile sticks out of the problem; warps whose part of it holds no valid row or column skip the math (a sector of 68
+// rows is one full row of tiles plus one whose lower two warps have nothing to do).  Finer skipping — guarding every 8 x 8
+// slice — was measured and rejected: predicated DMMAs lose the issue cadence of the unguarded loop, an edge tile then costs
+// MORE than multiplying its padding (U1 D=16384 P2 float64: 3.07 -> 4.63 ms; profiles/kernel_table_r02_edge_skip.json).
 template <bool CPLX, int AL, int BL, int BM, int BN, bool EDGE>
 __device__ __forceinline__ void ws_consume_tile(const GemmArgs& g, const GemmProblem& P, const GemmTile& T, int tile_index, int it_begin,
                                                 int it_end, int n_iters, uint32_t smem, uint32_t bars, int stage_bytes, uint32_t& it_glob) {
@@ -615,60 +615,17 @@ __device__ __forceinline__ void ws_consume_tile(const GemmArgs& g, const GemmPro
     for (int i = 0; i < MT; ++i) aoff[i] = frag_offset<CPLX, AL, BM>(wm0 + i * 8 + lx, lk);
 #pragma unroll
     for (int j = 0; j < NT; ++j) boff[j] = A_BYTES + frag_offset<CPLX, BL, BN>(wn0 + j * 8 + lx, lk);
-    // slices of this warp's tile that hold valid rows / columns (warp-uniform)
-    int mt_valid = MT, nt_valid = NT;
-    if constexpr (EDGE) {
-        mt_valid = min(MT, max(0, (P.M - T.m0 - wm0 + 7) >> 3));
-        nt_valid = min(NT, max(0, (P.N - T.n0 - wn0 + 7) >> 3));
-        if (mt_valid == 0 || nt_valid == 0) mt_valid = nt_valid = 0;
-    }
+    // a warp whose 32 x 64 (16 x 16 ...) part of an edge tile lies completely outside the problem only keeps the ring moving
+    const bool idle = EDGE && (T.m0 + wm0 >= P.M || T.n0 + wn0 >= P.N);
 
     for (int it = 0; it < n_iters; ++it) {
         const uint32_t stage = it_glob % kStages, phase = (it_glob / kStages) & 1;
         mbar_wait(bars + stage * 8, phase);                              // the stage has landed
         const uint32_t sa = smem + stage * stage_bytes;
+        if (!idle) {
 #pragma unroll
         for (int ks = 0; ks < KSTEPS; ++ks) {
-            if constexpr (EDGE) {
-                if constexpr (!CPLX) {
-                    double bf[NT];
-#pragma unroll
-                    for (int j = 0; j < NT; ++j)
-                        bf[j] = j < nt_valid ? lds64(sa + (BL == KC ? (boff[j] ^ (ks * 32)) : (boff[j] + ks * 4 * BN * ES))) : 0.0;
-#pragma unroll
-                    for (int i = 0; i < MT; ++i) {
-                        if (i < mt_valid) {
-                            const double af = lds64(sa + (AL == KC ? (aoff[i] ^ (ks * 32)) : (aoff[i] + ks * 4 * BM * ES)));
-#pragma unroll
-                            for (int j = 0; j < NT; ++j)
-                                if (j < nt_valid) dmma(acc[i][j][0], acc[i][j][1], af, bf[j]);
-                        }
-                    }
-                } else {
-                    double2 bf[NT];
-#pragma unroll
-                    for (int j = 0; j < NT; ++j) {
-                        bf[j] = j < nt_valid ? lds128(sa + (BL == KC ? (boff[j] ^ (ks * 64)) : (boff[j] + ks * 4 * BN * ES))) : make_double2(0.0, 0.0);
-                        bf[j].y = flip_sign(bf[j].y, sgnB);
-                    }
-#pragma unroll
-                    for (int i = 0; i < MT; ++i) {
-                        if (i < mt_valid) {
-                            double2 af = lds128(sa + (AL == KC ? (aoff[i] ^ (ks * 64)) : (aoff[i] + ks * 4 * BM * ES)));
-                            af.y = flip_sign(af.y, sgnA);
-                            const double naf = flip_sign(af.y, 0x80000000u);
-#pragma unroll
-                            for (int j = 0; j < NT; ++j)
-                                if (j < nt_valid) {
-                                    dmma(acc[i][j][0], acc[i][j][1], af.x, bf[j].x);
-                                    dmma(acc[i][j][0], acc[i][j][1], naf, bf[j].y);
-                                    dmma(acc[i][j][2], acc[i][j][3], af.x, bf[j].y);
-                                    dmma(acc[i][j][2], acc[i][j][3], af.y, bf[j].x);
-                                }
-                        }
-                    }
-                }
-            } else if constexpr (!CPLX) {
+            if constexpr (!CPLX) {
                 double af[MT], bf[NT];
 #pragma unroll
                 for (int i = 0; i < MT; ++i) af[i] = lds64(sa + (AL == KC ? (aoff[i] ^ (ks * 32)) : (aoff[i] + ks * 4 * BM * ES)));
@@ -702,6 +659,7 @@ __device__ __forceinline__ void ws_consume_tile(const GemmArgs& g, const GemmPro
                         dmma(acc[i][j][2], acc[i][j][3], af[i].y, bf[j].x);
                     }
             }
+        }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bars + (kStages + stage) * 8);        // this warp is done reading the stage
