@@ -134,6 +134,21 @@ int yb_ew_run(const yb_ew_plan* plan, void* dst, const void* src0, const void* s
 void yb_ew_plan_destroy(yb_ew_plan* plan);
 
 /* ------------------------------------------------------------------------------------------------
+ * Batched SVD of small charge sectors (one-sided Jacobi in shared memory, one CTA per sector, one launch per block matrix).
+ *   reference interface replaced: the per-sector loop of backend.svd / svdvals for sectors up to 64 x 64
+ *   (yastn/backend/_backend_torch_backwards.py:26-39, yastn/backend/backend_torch.py:322-327; torch.linalg.svd per sector).
+ * recs is an nrec x 6 int64 table [offA, m, n, offU, offS, offV] (element offsets): A row-major m x n inside `A`, U row-major
+ * m x k inside `U`, k singular values (descending, float64) inside `S`, Vh row-major k x n inside `Vh`, k = min(m, n) <= 64.
+ * status (nrec int32, device): 0 ok, 1 not converged within max_sweeps, 2 a singular value is exactly zero (the vectors of that
+ * sector are not orthonormal; refactorise it with another routine).  vectors = 0: singular values only.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct yb_svd_plan yb_svd_plan;
+int yb_svd_plan_create(const int64_t* recs, int64_t nrec, int itemsize, int device, yb_svd_plan** out);
+int yb_svd_run(const yb_svd_plan* plan, const void* A, void* U, void* S, void* Vh, void* status, int max_sweeps, int vectors,
+               void* stream);
+void yb_svd_plan_destroy(yb_svd_plan* plan);
+
+/* ------------------------------------------------------------------------------------------------
  * Device-side sector matching (meta pass).  All pointers are DEVICE pointers.  A blocks (table order = the reference's
  * block order, outgoing charges first) are joined with B blocks (sorted by contracted charge first) on the contracted
  * charge a_key / b_key ([n, key_width] int64); a_dims = [na, 2] (M, K), b_dims = [nb, 2] (K, N), *_off = block offsets.

@@ -101,10 +101,12 @@ def test_decompositions_through_yastn_match_stock_torch(device, dtype):
     # svd with the reference's driver: same cuSOLVER routine per sector on both sides -> identical bits; reconstruction against
     # the numpy input (the default driver, gesvdp for large sectors, is tested in test_gesvdp_sectors_cuda)
     decomp.set_svd_driver("gesvd")
+    decomp.set_jacobi_max(0)
     try:
         U, S, V = yastn.svd(a, axes=((0, 1), (2, 3)), sU=1)
     finally:
         decomp.set_svd_driver("gesvdp")
+        decomp.set_jacobi_max(64)
     Ur, Sr, Vr = yastn.svd(r, axes=((0, 1), (2, 3)), sU=1)
     for x, y in ((U, Ur), (S, Sr), (V, Vr)):
         assert x.struct == y.struct and x.slices == y.slices
@@ -141,6 +143,7 @@ def test_sector_parallel_svd_many_sectors_cuda():
     meta, n, sizes = _svd_meta(shapes)
     fns = decomp.make(stock)
     decomp.set_svd_driver("gesvd")
+    decomp.set_jacobi_max(0)
     try:
         for dtype in (torch.float64, torch.complex128):
             data = torch.randn(n, dtype=dtype, device="cuda")
@@ -152,6 +155,52 @@ def test_sector_parallel_svd_many_sectors_cuda():
             assert torch.equal(fns["svdvals"](data, meta, sizes[1]), stock.svdvals(data, meta, sizes[1]))
     finally:
         decomp.set_svd_driver("gesvdp")
+        decomp.set_jacobi_max(64)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float64, torch.complex128])
+def test_batched_jacobi_svd_small_sectors_cuda(dtype):
+    """Sectors up to 64 x 64 are factorised by ONE launch of the one-sided Jacobi kernel (csrc/yb_svd.cu).  Against numpy's
+    LAPACK SVD of the same data: singular values to 1e-13 * S_max (1e-14 absolute on a spectrum graded over twelve decades),
+    reconstruction and orthogonality to 1e-13, descending order, bit-identical
+    repeats; a rank-deficient sector and a zero sector are reported by the kernel and redone by the library routine."""
+    rng = np.random.default_rng(2)
+    shapes = [(1, 1), (1, 7), (7, 1), (2, 2), (8, 8), (17, 33), (33, 17), (64, 64), (64, 3), (3, 64), (31, 32), (50, 50), (63, 64), (5, 5), (6, 6)]
+    meta, n, sizes = _svd_meta(shapes)
+    fns = decomp.make(stock)
+    data = torch.randn(n, dtype=dtype, device="cuda")
+    # sector 11 (50 x 50): graded spectrum; sector 13 (5 x 5): rank 2; sector 14 (6 x 6): all zero
+    sl, D = meta[11][0], meta[11][1]
+    Q1, _ = torch.linalg.qr(torch.randn(50, 50, dtype=dtype, device="cuda"))
+    Q2, _ = torch.linalg.qr(torch.randn(50, 50, dtype=dtype, device="cuda"))
+    sg = torch.logspace(0, -12, 50, dtype=torch.float64, device="cuda")
+    data[sl[0]:sl[1]] = ((Q1 * sg.to(dtype)) @ Q2).reshape(-1)
+    sl = meta[13][0]
+    low = torch.randn(5, 2, dtype=dtype, device="cuda") @ torch.randn(2, 5, dtype=dtype, device="cuda")
+    data[sl[0]:sl[1]] = low.reshape(-1)
+    sl = meta[14][0]
+    data[sl[0]:sl[1]] = 0
+    s0 = decomp.stats()
+    U, S, Vh = fns["svd"](data, meta, sizes)
+    U2, S2, Vh2 = fns["svd"](data, meta, sizes)
+    assert torch.equal(U, U2) and torch.equal(S, S2) and torch.equal(Vh, Vh2)
+    s1 = decomp.stats()
+    assert s1.get("jacobi_calls", 0) - s0.get("jacobi_calls", 0) == 2 and s1.get("jacobi_sectors", 0) - s0.get("jacobi_sectors", 0) == 2 * len(shapes)
+    host = data.cpu().numpy()
+    for i, (slA, DA, slU, DU, slS, slV, DV) in enumerate(meta):
+        A = host[slA[0]:slA[1]].reshape(DA)
+        s = S[slS[0]:slS[1]].cpu().numpy()
+        u = U[slU[0]:slU[1]].view(DU).cpu().numpy()
+        vh = Vh[slV[0]:slV[1]].view(DV).cpu().numpy()
+        sr = np.linalg.svd(A, compute_uv=False)
+        smax = max(sr.max(), 1e-300)
+        assert np.all(np.diff(s) <= 0) and np.abs(s - sr).max() <= 1e-13 * smax, (i, DA)
+        assert np.linalg.norm((u * s) @ vh - A) <= 1e-13 * max(np.linalg.norm(A), 1e-300), (i, DA)
+        k = s.size
+        assert np.linalg.norm(u.conj().T @ u - np.eye(k)) <= 1e-13 * k and np.linalg.norm(vh @ vh.conj().T - np.eye(k)) <= 1e-13 * k, (i, DA)
+    s = S[meta[11][4][0]:meta[11][4][1]].cpu().numpy()
+    assert np.abs(s - sg.cpu().numpy()).max() <= 1e-14           # the matrix itself is only defined to eps * S_max
 
 
 @pytest.mark.gpu

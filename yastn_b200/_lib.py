@@ -29,6 +29,9 @@ SIGNATURES = {
     "yb_ew_plan_info": (_c.c_int, [_vp, _i64p]),
     "yb_ew_run": (_c.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "yb_ew_plan_destroy": (None, [_vp]),
+    "yb_svd_plan_create": (_c.c_int, [_vp, _c.c_int64, _c.c_int, _c.c_int, _c.POINTER(_vp)]),
+    "yb_svd_run": (_c.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c.c_int, _c.c_int, _vp]),
+    "yb_svd_plan_destroy": (None, [_vp]),
     "yb_peer_alloc": (_c.c_int, [_c.c_int64, _c.c_int, _c.POINTER(_vp), _vp]),
     "yb_peer_open": (_c.c_int, [_vp, _c.c_int, _c.POINTER(_vp)]),
     "yb_peer_close": (_c.c_int, [_vp]),

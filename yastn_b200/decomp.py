@@ -20,10 +20,12 @@ bit-identical to the reference loop on the same device; only the schedule change
 Inputs that require grad keep the reference's autograd implementations (the pool is a forward-only schedule), CPU
 tensors keep the reference's loop.
 """
+import ctypes
 import os
 import threading
 from concurrent.futures import ThreadPoolExecutor
 
+import numpy as np
 import torch
 
 _WORKERS = int(os.environ.get("YASTN_B200_DECOMP_WORKERS", "8"))
@@ -167,6 +169,48 @@ def run_sectors(fn, recs, costs, device):
         raise err
 
 
+# ---- small sectors: ONE launch of the batched one-sided Jacobi kernel (csrc/yb_svd.cu) -------------------------------------
+_JACOBI_MAX = int(os.environ.get("YASTN_B200_JACOBI_MAX", "64"))     # sectors up to this many rows and columns; 0 disables
+_JACOBI_SWEEPS = 30
+_jacobi_plans = {}
+
+
+def set_jacobi_max(n):
+    global _JACOBI_MAX
+    _JACOBI_MAX = int(n)
+
+
+def _jacobi_svd(data, meta, small, Udata, Sdata, Vhdata, vectors=True):
+    """Factorise the sectors ``meta[i], i in small`` in one launch, straight into the output tensors.  Returns the indices that
+    must be redone by the library routine (not converged / exactly singular: the kernel reports, it never guesses)."""
+    from . import plans, _lib
+    dev = data.device
+    key = (id(meta), tuple(small) if len(small) < len(meta) else None, data.dtype, dev.index, vectors)
+    ent = _jacobi_plans.get(key)
+    if ent is None or ent[0] is not meta:
+        if vectors:
+            recs = [[meta[i][0][0], meta[i][1][0], meta[i][1][1], meta[i][2][0], meta[i][4][0], meta[i][5][0]] for i in small]
+        else:      # svdvals meta: (sl, D, slU, DU, slS, ...)
+            recs = [[meta[i][0][0], meta[i][1][0], meta[i][1][1], 0, meta[i][4][0], 0] for i in small]
+        if len(_jacobi_plans) > 4096:
+            _jacobi_plans.clear()
+        ent = (meta, plans.SvdPlan(np.array(recs, dtype=np.int64), 16 if data.is_complex() else 8, dev.index))
+        _jacobi_plans[key] = ent
+    if data.is_conj():
+        data = data.resolve_conj()
+    data = data if data.is_contiguous() else data.contiguous()
+    status = torch.empty(len(small), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        ent[1].run(data.data_ptr(), Udata.data_ptr() if vectors else None, Sdata.data_ptr(), Vhdata.data_ptr() if vectors else None,
+                   status.data_ptr(), _JACOBI_SWEEPS, vectors, st)
+    with _pools_lock:
+        _stats["jacobi_calls"] = _stats.get("jacobi_calls", 0) + 1
+        _stats["jacobi_sectors"] = _stats.get("jacobi_sectors", 0) + len(small)
+    bad = status.nonzero().reshape(-1).tolist()        # one host synchronisation per block matrix (the reference has one per sector)
+    return [small[i] for i in bad]
+
+
 def _svd_cost(D):
     m, n = D
     return m * n * min(m, n)
@@ -193,7 +237,15 @@ def make(stock):
             Udata[slU[0]:slU[1]].view(DU).copy_(U)
             Sdata[slS[0]:slS[1]].copy_(S)
             Vhdata[slV[0]:slV[1]].view(DV).copy_(Vh)
-        run_sectors(one, meta, [_svd_cost(m[1]) for m in meta], data.device)
+        rest = list(range(len(meta)))
+        if _JACOBI_MAX > 0 and not fullrank_uv and data.dtype in (torch.float64, torch.complex128):
+            small = [i for i in rest if max(meta[i][1]) <= min(_JACOBI_MAX, 64) and min(meta[i][1]) >= 1]
+            if small:
+                redo = _jacobi_svd(data, meta, small, Udata, Sdata, Vhdata)
+                done = set(small) - set(redo)
+                rest = [i for i in rest if i not in done]
+        recs = meta if len(rest) == len(meta) else [meta[i] for i in rest]
+        run_sectors(one, recs, [_svd_cost(m[1]) for m in recs], data.device)
         return Udata, Sdata, Vhdata
 
     def svdvals(data, meta, sizeS, **kwargs):

@@ -746,6 +746,30 @@ class EwPlan:
             pass
 
 
+class SvdPlan:
+    """Device plan of one batched small-sector SVD launch (owns the C handle)."""
+
+    def __init__(self, recs, itemsize, device):
+        lib = _lib.load()
+        self._lib = lib
+        self.handle = ctypes.c_void_p()
+        recs = np.ascontiguousarray(recs, dtype=I64).reshape(-1, 6)
+        self.nrec = recs.shape[0]
+        _lib.check(lib.yb_svd_plan_create(_ptr(recs), self.nrec, itemsize, device, ctypes.byref(self.handle)))
+
+    def run(self, a_ptr, u_ptr, s_ptr, vh_ptr, status_ptr, max_sweeps, vectors, stream):
+        rc = self._lib.yb_svd_run(self.handle, a_ptr, u_ptr, s_ptr, vh_ptr, status_ptr, max_sweeps, 1 if vectors else 0, stream)
+        if rc:
+            _lib.check(rc)
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self._lib.yb_svd_plan_destroy(self.handle)
+        except Exception:
+            pass
+
+
 class GemmPlan:
     """Device plan of one grouped-GEMM launch (owns the C handle)."""
 
