@@ -92,9 +92,10 @@ def svd(A):
     k = n
     with torch.cuda.device(dev):
         lib.cusolverDnSetStream(handle, ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
-        a = A.t().contiguous()                         # memory = A in column-major order, lda = m
-        if a.is_conj():
-            a = a.resolve_conj()
+        # gesvdp DESTROYS its input (it is overwritten by the polar factor): always a private column-major copy (lda = m).
+        # (A.t().contiguous() aliases the caller's storage when A is the transposed view of a contiguous matrix.)
+        a = torch.empty((n, m), dtype=A.dtype, device=dev)
+        a.copy_(A.t())                                 # copy_ also resolves a lazy conj bit
         U = torch.empty((k, m), dtype=A.dtype, device=dev)      # column-major m x k
         V = torch.empty((k, n), dtype=A.dtype, device=dev)      # column-major n x k
         S = torch.empty(k, dtype=torch.float64, device=dev)
