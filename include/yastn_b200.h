@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define YB_ABI_VERSION 3
+#define YB_ABI_VERSION 4
 
 /* element types */
 #define YB_F64 0
@@ -161,6 +161,48 @@ int64_t yb_match_scratch_elems(int64_t na, int64_t nb);
 int yb_match_sectors(const int64_t* a_key, const int64_t* a_dims, const int64_t* a_off, int64_t na,
                      const int64_t* b_key, const int64_t* b_dims, const int64_t* b_off, int64_t nb, int key_width,
                      int64_t capacity, int64_t* problems, int64_t* segments, int64_t* result, int64_t* scratch, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Host-side meta pass (no device calls): the reference's meta tuples, flattened depth-first to int64 tables, become the
+ * record tables of the plans above.  A launch-bound run (DMRG at D=64 meets ~20 new block structures per bond) spends its
+ * time here, not in the kernels.  Every call leaves its result in a thread-local buffer: read its length with
+ * yb_tables_result_size() and copy it out with yb_tables_result_fetch().
+ *   yb_tables_merge   : records of backend.transpose_and_merge (loop: _backend_torch_backwards.py:340-364) from
+ *                       meta_mrg rows [tn(T), slo(2), Do(r), Dslc(2g), Drsh(g)] and meta_new rows [tn(T), Dn(g), sln(2)]
+ *                       (yastn/tensor/_merging.py:137-187), plus zero-fill records for the cells no source block covers.
+ *                       Result [status, rank, covered, nrec, recs...]; status 1: records not grouped in meta_new order (pass
+ *                       grp_in), 2: zero-fill records not built (clear the destination instead).
+ *   yb_tables_scatter : tables of yb_gemm_plan_create_scatter from meta_unmerge rows [sln(2), Dn(gn), slo(2), Do(2), r0, r1,
+ *                       c0, c1] (yastn/tensor/_merging.py:528-549) and meta_dot rows (12 wide); shift: optional per-record
+ *                       destination shift.  Result [nprob, ng, nrow, ncol, ndst, scat_index, row_ptr, row_cuts, col_ptr,
+ *                       col_cuts, dst_ptr, dst].
+ *   yb_tables_add     : LINCOMB records of backend.add / sub (yastn/backend/backend_torch.py:518-534) from rows
+ *                       [operand, c0, c1, a0].  Result [nrounds, {nrec, nslots, slots[4], recs(nrec x 16)}...].
+ * ---------------------------------------------------------------------------------------------- */
+int64_t yb_tables_result_size(void);
+int yb_tables_result_fetch(int64_t* out, int64_t n);
+int yb_tables_merge(const int64_t* mrg, int64_t n, int64_t wm, const int64_t* neu, int64_t nnew, int64_t wn,
+                    const int64_t* order, int r, int g, int T, const int64_t* grp_in, int zero_records);
+int yb_tables_scatter(const int64_t* um, int64_t n, int gn, const int64_t* md, int64_t nprob, const int64_t* shift);
+int yb_tables_add(const int64_t* ops, int64_t nrec, int64_t n_ops, const int64_t* signs);
+
+/* ------------------------------------------------------------------------------------------------
+ * Chains: a recorded sequence of copy / grouped-GEMM runs (several tensordots in a row) replayed by one call.
+ *   reference call sites: the four tensordots of Env_mps_mpo_mps.Heff2 (yastn/tn/mps/_env.py:512-518), Heff1 (:506-510),
+ *   update_env_to_last / _to_first (:496-504) — applied again and again to operands of unchanged block structure inside eigs.
+ * steps is an nsteps x 10 int64 table [kind, run flags, plan handle, slotA, offA, slotB, offB, slotC, offC, dst_elems]:
+ *   kind YB_CHAIN_COPY: yb_copy_run(plan, slots[slotA] + offA, slots[slotC] + offC, dst_elems, flags)
+ *   kind YB_CHAIN_GEMM: yb_gemm_run(plan, slots[slotA] + offA, slots[slotB] + offB, slots[slotC] + offC, flags)
+ * (offsets in bytes; slotB is ignored for copies).  slots are base device pointers supplied per run — the caller's operands,
+ * a scratch arena holding the intermediates, the result.  The chain borrows the plans: they must outlive it.
+ * ---------------------------------------------------------------------------------------------- */
+#define YB_CHAIN_COPY 0
+#define YB_CHAIN_GEMM 1
+typedef struct yb_chain yb_chain;
+int yb_chain_create(const int64_t* steps, int64_t nsteps, int64_t nslots, yb_chain** out);
+int yb_chain_run(const yb_chain* chain, void* const* slots, int64_t nslots, void* stream);
+int64_t yb_chain_steps(const yb_chain* chain);
+void yb_chain_destroy(yb_chain* chain);
 
 /* ------------------------------------------------------------------------------------------------
  * Peer arenas (multi-GPU, one process per GPU on one box).  The reference has no multi-GPU path for a

@@ -132,6 +132,22 @@ class CpuEwPlan:
         exec_ew(self.recs, self.traces, dst, srcs, aux)
 
 
+class CpuChain:
+    """Interpreter of a chain's step table (include/yastn_b200.h, yb_chain_run) over the CPU plans above."""
+
+    def __init__(self, table, plan_list, nslots):
+        self.table, self.plans, self.nslots = np.array(table, dtype=np.int64), list(plan_list), nslots
+
+    def run(self, ptrs, stream):
+        assert len(ptrs) == self.nslots
+        for kind, flags, pi, sa, oa, sb, ob, sc, oc, n in self.table.tolist():
+            plan = self.plans[pi]
+            if kind == _lib.YB_CHAIN_COPY:
+                plan.run(ptrs[sa] + oa, ptrs[sc] + oc, n, flags, None)
+            else:
+                plan.run(ptrs[sa] + oa, ptrs[sb] + ob, ptrs[sc] + oc, flags, None)
+
+
 _saved = {}
 
 
@@ -149,6 +165,10 @@ def install():
     bk._check = check
     yastn_backend._native = lambda *ts: all(t.dtype in (torch.float64, torch.complex128) for t in ts)
     yastn_backend._on_gpu = yastn_backend._native
+    from yastn_b200 import chain
+    _saved.update(chain_runner=chain._NativeChain, chain_usable=chain._usable)
+    chain._NativeChain, chain._usable = CpuChain, (lambda d: True)
+    chain.clear()
     bk.clear_plan_cache()
 
 
@@ -158,5 +178,8 @@ def uninstall():
     plans.CopyPlan, plans.GemmPlan, plans.EwPlan = _saved["CopyPlan"], _saved["GemmPlan"], _saved["EwPlan"]
     bk._on_device, bk._check, yastn_backend._native = _saved["on_device"], _saved["check"], _saved["native"]
     yastn_backend._on_gpu = _saved["on_gpu"]
+    from yastn_b200 import chain
+    chain._NativeChain, chain._usable = _saved["chain_runner"], _saved["chain_usable"]
+    chain.clear()
     bk.clear_plan_cache()
     _saved.clear()

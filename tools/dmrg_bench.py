@@ -157,6 +157,7 @@ def main():
     ap.add_argument("--D0", type=int, default=None, help="bond dimension of the random initial MPS (default min(D, 32))")
     ap.add_argument("--shim", action="store_true", help="CPU table interpreter instead of the kernels (host-logic check, tests/cpu_shim.py)")
     ap.add_argument("--fused", action="store_true", help="b200 only: fuse dot+unmerge into one launch (yastn_backend.enable_fused_tensordot)")
+    ap.add_argument("--chains", action="store_true", help="b200 only: record / replay the tensordot chains of Heff and the environment updates (yastn_b200.chain)")
     ap.add_argument("--decomp-workers", type=int, default=None, help="b200 only: sector streams of svd/qr/eigh (1 = the reference's serial loop)")
     ap.add_argument("--profile", action="store_true", help="time every backend function (device-synchronised: perturbs the totals)")
     ap.add_argument("--gemm-roofline", action="store_true", help="CUDA-event time and FLOP count of every dot / dot_unmerge launch (no sync inside the sweep)")
@@ -181,6 +182,9 @@ def main():
         counts = yastn_backend.call_counts
         if args.fused:
             yastn_backend.enable_fused_tensordot()
+        if args.chains:
+            from yastn_b200 import chain
+            chain.enable()
     else:
         backend = args.backend
     device = "cpu" if args.backend == "np" else args.device
@@ -208,6 +212,9 @@ def main():
     line = {"model": args.model, "N": args.N, "D": args.D, "dtype": args.dtype, "backend": args.backend + ("+fused" if args.fused else ""), "device": device, "policy": args.policy,
             "sweep_s": times, "energy": energies, "bond_dims": max(psi.get_bond_dimensions()),
             "hot_calls": counts() if counts else None, "decomp_workers": args.decomp_workers}
+    if args.backend == "b200" and args.chains:
+        line["backend"] += "+chains"
+        line["chains"] = chain.stats()
     if roof is not None:
         line["gemm_roofline"] = roof()
     if args.profile:

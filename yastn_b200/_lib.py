@@ -32,6 +32,15 @@ SIGNATURES = {
     "yb_svd_plan_create": (_c.c_int, [_vp, _c.c_int64, _c.c_int, _c.c_int, _c.POINTER(_vp)]),
     "yb_svd_run": (_c.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c.c_int, _c.c_int, _vp]),
     "yb_svd_plan_destroy": (None, [_vp]),
+    "yb_tables_result_size": (_c.c_int64, []),
+    "yb_tables_result_fetch": (_c.c_int, [_vp, _c.c_int64]),
+    "yb_tables_merge": (_c.c_int, [_vp, _c.c_int64, _c.c_int64, _vp, _c.c_int64, _c.c_int64, _vp, _c.c_int, _c.c_int, _c.c_int, _vp, _c.c_int]),
+    "yb_tables_scatter": (_c.c_int, [_vp, _c.c_int64, _c.c_int, _vp, _c.c_int64, _vp]),
+    "yb_tables_add": (_c.c_int, [_vp, _c.c_int64, _c.c_int64, _vp]),
+    "yb_chain_create": (_c.c_int, [_vp, _c.c_int64, _c.c_int64, _c.POINTER(_vp)]),
+    "yb_chain_run": (_c.c_int, [_vp, _vp, _c.c_int64, _vp]),
+    "yb_chain_steps": (_c.c_int64, [_vp]),
+    "yb_chain_destroy": (None, [_vp]),
     "yb_peer_alloc": (_c.c_int, [_c.c_int64, _c.c_int, _c.POINTER(_vp), _vp]),
     "yb_peer_open": (_c.c_int, [_vp, _c.c_int, _c.POINTER(_vp)]),
     "yb_peer_close": (_c.c_int, [_vp]),
@@ -40,10 +49,11 @@ SIGNATURES = {
     "yb_match_sectors": (_c.c_int, [_vp, _vp, _vp, _c.c_int64, _vp, _vp, _vp, _c.c_int64, _c.c_int, _c.c_int64, _vp, _vp, _vp, _vp, _vp]),
 }
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 YB_F64, YB_C128 = 0, 1
 YB_COPY_ZERO_DST, YB_COPY_CONJ = 1, 2
 YB_GEMM_CONJ_A, YB_GEMM_CONJ_B = 1, 2
+YB_CHAIN_COPY, YB_CHAIN_GEMM = 0, 1
 
 _lib = None
 

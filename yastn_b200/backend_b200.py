@@ -72,9 +72,14 @@ def _on_device(dev, launch):
         launch(_stream(dev))
 
 
+_recorder = None        # yastn_b200.chain._Recorder while a chain of launches is being recorded
+
+
 def _run_copy(plan, src, dst, zero):
     raw, conj = _raw(src)
     flags = (_lib.YB_COPY_ZERO_DST if zero else 0) | (_lib.YB_COPY_CONJ if conj else 0)
+    if _recorder is not None:
+        _recorder.copy(plan, raw, dst, flags)
     _on_device(src.device, lambda st: plan.run(raw.data_ptr(), dst.data_ptr(), dst.numel(), flags, st))
 
 
@@ -82,6 +87,8 @@ def _run_gemm(plan, A, B, C, conj_a=False, conj_b=False):
     ra, ca = _raw(A)
     rb, cb = _raw(B)
     flags = (_lib.YB_GEMM_CONJ_A if (ca != conj_a) else 0) | (_lib.YB_GEMM_CONJ_B if (cb != conj_b) else 0)
+    if _recorder is not None:
+        _recorder.gemm(plan, ra, rb, C, flags)
     _on_device(C.device, lambda st: plan.run(ra.data_ptr(), rb.data_ptr(), C.data_ptr(), flags, st))
 
 
@@ -497,6 +504,8 @@ def vdot(Adata, Bdata, meta):
 # -------------------------------------------------------------------------------------------------
 
 def _run_ew(plan, dst, srcs, aux=None):
+    if _recorder is not None:
+        _recorder.unsupported("elementwise plan")
     _on_device(dst.device, lambda st: plan.run(dst.data_ptr(), [s.data_ptr() for s in srcs], None if aux is None else aux.data_ptr(), st))
 
 

@@ -49,24 +49,30 @@ def build(force=False, verbose=False):
     build_flatten(force)
     if not force and not needs_build():
         return LIB
-    objs = []
-    log = []
-    for src in sources():
+    hdr_t = max(os.path.getmtime(d) for d in glob.glob(os.path.join(CSRC, "*.h")) + [os.path.join(HERE, "..", "include", "yastn_b200.h")])
+
+    def compile_one(src):
         obj = os.path.join(CSRC, os.path.basename(src)[:-3] + ".o")
-        cmd = [NVCC] + FLAGS + ["-c", src, "-o", obj]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        log.append(r.stderr)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_t):
+            return obj, ""                       # up to date
+        r = subprocess.run([NVCC] + FLAGS + ["-c", src, "-o", obj], capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError(f"nvcc failed on {src}")
-        objs.append(obj)
+        return obj, r.stderr
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:      # the translation units are independent
+        done = list(ex.map(compile_one, sources()))
+    objs = [o for o, _ in done]
+    log = [l for _, l in done]
     cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("link failed")
-    with open(os.path.join(CSRC, "ptxas.log"), "w") as f:
-        f.write("\n".join(log))
+    if all(log):            # a partial rebuild keeps the register / spill report of the last full build
+        with open(os.path.join(CSRC, "ptxas.log"), "w") as f:
+            f.write("\n".join(log))
     if verbose:
         print("\n".join(log))
     return LIB

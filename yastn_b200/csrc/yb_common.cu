@@ -28,7 +28,10 @@ struct DevicePool {
     std::vector<void*> pending[48];   // released by a destroyed plan; kernels reading them may still be queued
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t copy_done = nullptr;
+    char* staging = nullptr;          // pinned host buffer of the batched table uploads
+    size_t staging_bytes = 0;
 };
+constexpr size_t kStagingMax = 8u << 20;
 DevicePool& pool_of(int device) {
     static DevicePool pools[64];
     return pools[(device >= 0 && device < 64) ? device : 0];
@@ -80,6 +83,64 @@ int pool_upload(int device, void* dst, const void* host, size_t bytes) {
     YB_CUDA(cudaMemcpyAsync(dst, host, bytes, cudaMemcpyHostToDevice, p.copy_stream));
     YB_CUDA(cudaEventRecord(p.copy_done, p.copy_stream));
     YB_CUDA(cudaEventSynchronize(p.copy_done));   // the host waits for this copy only, not for the compute streams
+    return kOk;
+}
+
+int TableBatch::commit() {
+    size_t total = 0;
+    for (auto& it : items) total += (it.bytes + 255) & ~(size_t)255;
+    if (total == 0) return kOk;
+    int device = 0;
+    if (cudaGetDevice(&device) != cudaSuccess) return fail(kErrCuda, "cudaGetDevice failed");
+    if (total > kStagingMax) {     // large plans: one block and one (pageable) copy per table, as before
+        for (auto& it : items) {
+            int rc = it.table->upload(it.host, it.bytes);
+            if (rc != kOk) return rc;
+        }
+        return kOk;
+    }
+    void* block = nullptr;
+    size_t cap = 0;
+    int rc = pool_alloc(device, total, &block, &cap);
+    if (rc != kOk) return rc;
+    DevicePool& p = pool_of(device);
+    std::lock_guard<std::mutex> lk(p.mu);
+    bool first = true;
+    size_t off = 0;
+    // hand the block out before anything can fail: the plan's destroy path then returns it to the pool
+    for (auto& it : items) {
+        DeviceTable& t = *it.table;
+        t.bytes = it.bytes;
+        t.device = device;
+        if (it.bytes == 0) continue;
+        t.ptr = (char*)block + off;
+        t.owner = first;
+        t.cap = first ? cap : 0;
+        first = false;
+        off += (it.bytes + 255) & ~(size_t)255;
+    }
+    if (!p.copy_stream) {
+        YB_CUDA(cudaStreamCreateWithFlags(&p.copy_stream, cudaStreamNonBlocking));
+        YB_CUDA(cudaEventCreateWithFlags(&p.copy_done, cudaEventDisableTiming));
+    }
+    if (p.staging_bytes < total) {
+        if (p.staging) cudaFreeHost(p.staging);
+        p.staging = nullptr;
+        p.staging_bytes = 0;
+        size_t want = 1u << 16;
+        while (want < total) want <<= 1;
+        YB_CUDA(cudaHostAlloc((void**)&p.staging, want, cudaHostAllocDefault));
+        p.staging_bytes = want;
+    }
+    off = 0;
+    for (auto& it : items) {
+        if (it.bytes == 0) continue;
+        memcpy(p.staging + off, it.host, it.bytes);
+        off += (it.bytes + 255) & ~(size_t)255;
+    }
+    YB_CUDA(cudaMemcpyAsync(block, p.staging, off, cudaMemcpyHostToDevice, p.copy_stream));
+    YB_CUDA(cudaEventRecord(p.copy_done, p.copy_stream));
+    YB_CUDA(cudaEventSynchronize(p.copy_done));   // the staging buffer is free again; the host waited for this copy only
     return kOk;
 }
 

@@ -46,6 +46,7 @@ struct DeviceTable {
     void* ptr = nullptr;
     size_t bytes = 0, cap = 0;
     int device = 0;
+    bool owner = true;      // false: a sub-range of the block another table of the same plan owns (TableBatch)
     int upload(const void* host, size_t nbytes) {
         bytes = nbytes;
         if (nbytes == 0) return kOk;
@@ -55,9 +56,23 @@ struct DeviceTable {
         return pool_upload(device, ptr, host, nbytes);
     }
     void release() {
-        if (ptr) pool_free(device, ptr, cap);
+        if (ptr && owner) pool_free(device, ptr, cap);
         ptr = nullptr;
     }
+};
+
+// All tables of one plan in ONE pool block filled by ONE host->device copy (through a pinned staging buffer): creating a plan
+// costs one copy + one event wait instead of one per table (plan creation is what a D=64 DMRG sweep spends its time on:
+// ~20 new structures per bond, profiles/host_profile_r02.txt).  Sub-ranges are 256-byte aligned.
+struct TableBatch {
+    struct Item {
+        DeviceTable* table;
+        const void* host;
+        size_t bytes;
+    };
+    std::vector<Item> items;
+    void add(DeviceTable& t, const void* host, size_t bytes) { items.push_back({&t, host, bytes}); }
+    int commit();
 };
 
 // Division by a run-time invariant (valid for numerators < 2^31).

@@ -882,9 +882,13 @@ extern "C" int yb_copy_plan_create(const int64_t* recs, int64_t nrec, int rank, 
     cudaGetDevice(&prev);
     int rc = kOk;
     if (cudaSetDevice(device) != cudaSuccess) rc = fail(kErrCuda, "yb_copy_plan_create: cudaSetDevice(%d) failed", device);
-    if (rc == kOk) rc = plan->recs.upload(drecs.data(), drecs.size() * sizeof(CopyRec));
-    if (rc == kOk) rc = plan->items.upload(items.data(), items.size() * sizeof(CopyItem));
-    if (rc == kOk) rc = plan->runs.upload(runs.data(), runs.size() * sizeof(CopyRun));
+    if (rc == kOk) {
+        TableBatch up;
+        up.add(plan->recs, drecs.data(), drecs.size() * sizeof(CopyRec));
+        up.add(plan->items, items.data(), items.size() * sizeof(CopyItem));
+        up.add(plan->runs, runs.data(), runs.size() * sizeof(CopyRun));
+        rc = up.commit();
+    }
     if (rc == kOk) {
         plan->grid = std::min((nwarp_items + kCopyWarps - 1) / kCopyWarps, sms * 4);
         plan->grid_tiled = std::min((int)cta_items.size(), sms * 4);

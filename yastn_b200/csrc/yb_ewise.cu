@@ -249,8 +249,12 @@ extern "C" int yb_ew_plan_create(const int64_t* recs, int64_t nrec, const int64_
     cudaGetDevice(&prev);
     int rc = kOk;
     if (cudaSetDevice(device) != cudaSuccess) rc = fail(kErrCuda, "yb_ew_plan_create: cudaSetDevice(%d) failed", device);
-    if (rc == kOk) rc = plan->pieces.upload(pieces.data(), pieces.size() * sizeof(EwPiece));
-    if (rc == kOk) rc = plan->traces.upload(ht.data(), ht.size() * sizeof(EwTrace));
+    if (rc == kOk) {
+        TableBatch up;
+        up.add(plan->pieces, pieces.data(), pieces.size() * sizeof(EwPiece));
+        up.add(plan->traces, ht.data(), ht.size() * sizeof(EwTrace));
+        rc = up.commit();
+    }
     if (rc == kOk) {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);

@@ -1195,14 +1195,18 @@ int create_plan(const int64_t* problems, int64_t nprob, const int64_t* segments,
             plan->grid = (int)hr.size();
         }
     }
-    if (rc == kOk) rc = plan->problems.upload(hp.data(), hp.size() * sizeof(GemmProblem));
-    if (rc == kOk) rc = plan->segments.upload(hs.data(), hs.size() * sizeof(GemmSegment));
-    if (rc == kOk) rc = plan->tiles.upload(ht.data(), ht.size() * sizeof(GemmTile));
-    if (rc == kOk) rc = plan->ranges.upload(hr.data(), hr.size() * sizeof(CtaRange));
-    if (rc == kOk) rc = plan->scat.upload(hsc.data(), hsc.size() * sizeof(ScatterInfo));
-    if (rc == kOk) rc = plan->rowinfo.upload(hrow.data(), hrow.size() * sizeof(int2));
-    if (rc == kOk) rc = plan->colinfo.upload(hcol.data(), hcol.size() * sizeof(int4));
-    if (rc == kOk) rc = plan->dstpool.upload(hdst.data(), hdst.size() * sizeof(int64_t));
+    if (rc == kOk) {
+        TableBatch up;     // one pool block, one copy
+        up.add(plan->problems, hp.data(), hp.size() * sizeof(GemmProblem));
+        up.add(plan->segments, hs.data(), hs.size() * sizeof(GemmSegment));
+        up.add(plan->tiles, ht.data(), ht.size() * sizeof(GemmTile));
+        up.add(plan->ranges, hr.data(), hr.size() * sizeof(CtaRange));
+        up.add(plan->scat, hsc.data(), hsc.size() * sizeof(ScatterInfo));
+        up.add(plan->rowinfo, hrow.data(), hrow.size() * sizeof(int2));
+        up.add(plan->colinfo, hcol.data(), hcol.size() * sizeof(int4));
+        up.add(plan->dstpool, hdst.data(), hdst.size() * sizeof(int64_t));
+        rc = up.commit();
+    }
     if (rc == kOk && plan->nsplit > 0) {
         plan->ws_slots = max_grid;
         int coop = 0;

@@ -222,8 +222,10 @@ int panel_create(const std::vector<GemmProblem>& hp, const std::vector<GemmSegme
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     plan->grid = (int)std::max<int64_t>(1, std::min<int64_t>((parts + kPnWarps - 1) / kPnWarps, (int64_t)sms * 4));
-    int rc = plan->probs.upload(probs.data(), probs.size() * sizeof(PnProb));
-    if (rc == kOk) rc = plan->pstart.upload(pstart.data(), pstart.size() * sizeof(int64_t));
+    TableBatch up;
+    up.add(plan->probs, probs.data(), probs.size() * sizeof(PnProb));
+    up.add(plan->pstart, pstart.data(), pstart.size() * sizeof(int64_t));
+    int rc = up.commit();
     if (rc != kOk) {
         panel_destroy(plan);
         return rc;

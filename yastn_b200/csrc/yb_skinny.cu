@@ -414,9 +414,11 @@ int skinny_create(const std::vector<GemmProblem>& hp, const std::vector<GemmSegm
     }
     plan->nwarps = (int)warps.size();
     plan->nruns = nruns;
-    int rc = plan->parts.upload(parts.data(), parts.size() * sizeof(SkPart));
-    if (rc == kOk) rc = plan->warps.upload(warps.data(), warps.size() * sizeof(SkWarp));
-    if (rc == kOk) rc = plan->runs.upload(runs.data(), runs.size() * sizeof(SkRuns));
+    TableBatch up;
+    up.add(plan->parts, parts.data(), parts.size() * sizeof(SkPart));
+    up.add(plan->warps, warps.data(), warps.size() * sizeof(SkWarp));
+    up.add(plan->runs, runs.data(), runs.size() * sizeof(SkRuns));
+    int rc = up.commit();
     if (rc != kOk) {
         skinny_destroy(plan);
         return rc;

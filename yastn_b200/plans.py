@@ -108,8 +108,8 @@ def _zero_records(grp, lo, hi, Dn_new, sln_new, rank):
     return np.array(out, dtype=I64).reshape(len(out), 2 + 3 * rank), zeros
 
 
-def merge_records(order, meta_new, meta_mrg, zero_records=True):
-    """Copy records of transpose_and_merge.  Returns (recs, rank, covered): ``covered`` = destination elements the records
+def merge_records_np(order, meta_new, meta_mrg, zero_records=True):
+    """numpy statement of :func:`merge_records` (the C pass is checked against it on CPU).  Copy records of transpose_and_merge.  Returns (recs, rank, covered): ``covered`` = destination elements the records
     write, including the zero-fill records of uncovered cells (``zero_records``); a caller whose ``covered`` is below
     ``Dsize`` must clear the destination first."""
     n = len(meta_mrg)
@@ -292,8 +292,8 @@ def dot_backward_tables(meta_dot):
     return f(probA, 6), f(segA, 7), f(probB, 6), f(segB, 7)
 
 
-def unmerge_scatter_tables(meta_dot, meta_unmerge, dst_shift=None):
-    """Tables of the fused unmerge epilogue (include/yastn_b200.h, yb_gemm_plan_create_scatter).
+def unmerge_scatter_tables_np(meta_dot, meta_unmerge, dst_shift=None):
+    """numpy statement of :func:`unmerge_scatter_tables` (the C pass is checked against it on CPU).  Tables of the fused unmerge epilogue (include/yastn_b200.h, yb_gemm_plan_create_scatter).
 
     ``meta_unmerge`` (yastn/tensor/_merging.py:528-549) lists, for every merged C block ``slo`` of shape ``Do``,
     the rectangles ``((r0, r1), (c0, c1))`` that become the output blocks at ``sln``.  The rectangles of one merged
@@ -530,8 +530,8 @@ def _ew_array(recs):
     return np.array(recs, dtype=I64).reshape(len(recs), 16)
 
 
-def add_tables(metas, signs=None):
-    """Rounds of LINCOMB records of backend.add / sub (yastn/backend/backend_torch.py:518-534): ``new[sl_c] (+/-)= data_k[sl_a]``
+def add_tables_np(metas, signs=None):
+    """Python statement of :func:`add_tables` (the C pass is checked against it on CPU).  Rounds of LINCOMB records of backend.add / sub (yastn/backend/backend_torch.py:518-534): ``new[sl_c] (+/-)= data_k[sl_a]``
     for every (sl_c, sl_a) of ``metas[k]``; output ranges no operand writes stay zero (``newdata = torch.zeros``).
 
     One launch adds up to four operands; with more, later rounds read the running sum as their first source.  Returns a list
@@ -676,11 +676,99 @@ def trace_tables(order, meta):
 
 
 # -------------------------------------------------------------------------------------------------
+# meta pass in C (csrc/yb_tables.cu): the three builders a launch-bound sweep calls for every new block structure
+# -------------------------------------------------------------------------------------------------
+
+def _value_check(lib, rc):
+    if rc:
+        raise ValueError(lib.yb_last_error().decode())
+
+
+def _fetch(lib):
+    out = np.empty(lib.yb_tables_result_size(), dtype=I64)
+    _lib.check(lib.yb_tables_result_fetch(_ptr(out), out.size))
+    return out
+
+
+def merge_records(order, meta_new, meta_mrg, zero_records=True):
+    """Copy records of transpose_and_merge (one per source block, plus zero-fill records for the cells of the merged blocks
+    that no source block covers).  Returns (recs, rank, covered): ``covered`` = destination elements the records write; a
+    caller whose ``covered`` is below ``Dsize`` must clear the destination first."""
+    n, r = len(meta_mrg), len(order)
+    if n == 0:
+        return np.zeros((0, 2 + 3 * max(r, 1)), dtype=I64), max(r, 1), 0
+    lib = _lib.load()
+    g, T = len(meta_mrg[0][3]), len(meta_mrg[0][0])
+    mrg = _table(meta_mrg, n)
+    new = _table(meta_new, len(meta_new))
+    od = np.array(order, dtype=I64).reshape(-1)
+    _value_check(lib, lib.yb_tables_merge(_ptr(mrg), n, mrg.shape[1], _ptr(new), new.shape[0], new.shape[1] if new.size else T + g + 2,
+                                          _ptr(od), r, g, T, None, 1 if zero_records else 0))
+    out = _fetch(lib)
+    if out[0] == 1:      # records not grouped in the order of meta_new (the reference relies on it, _backend_torch_backwards.py:358)
+        index = {tn: i for i, (tn, _, _) in enumerate(meta_new)}
+        grp = np.array([index[m[0]] for m in meta_mrg], dtype=I64)
+        _value_check(lib, lib.yb_tables_merge(_ptr(mrg), n, mrg.shape[1], _ptr(new), new.shape[0], new.shape[1], _ptr(od), r, g, T, _ptr(grp),
+                                              1 if zero_records else 0))
+        out = _fetch(lib)
+    rank, covered, nrec = int(out[1]), int(out[2]), int(out[3])
+    return out[4:].reshape(nrec, 2 + 3 * rank), rank, covered
+
+
+def unmerge_scatter_tables(meta_dot, meta_unmerge, dst_shift=None):
+    """Tables of the fused unmerge epilogue (include/yastn_b200.h, yb_gemm_plan_create_scatter): the rectangles
+    ``((r0, r1), (c0, c1))`` of every merged C block (yastn/tensor/_merging.py:528-549) form a grid of row cuts x column cuts
+    and the GEMM epilogue writes every element straight to its output block.  ``dst_shift`` (one int64 per record of
+    ``meta_unmerge``) redirects a block into another rank's buffer (peer.PeerArena.shift).
+    Returns (scat_index[nprob], row_ptr, row_cuts, col_ptr, col_cuts, dst_ptr, dst)."""
+    nprob, n = len(meta_dot), len(meta_unmerge)
+    if n == 0:
+        return unmerge_scatter_tables_np(meta_dot, meta_unmerge, dst_shift)
+    if len(meta_unmerge[0][3]) != 2:
+        raise ValueError("fused unmerge needs matrix-shaped source blocks")
+    lib = _lib.load()
+    gn = len(meta_unmerge[0][1])
+    um = _table(meta_unmerge, n)
+    md = _table(meta_dot, nprob)
+    if um.shape[1] != 10 + gn or (nprob and md.shape[1] != 12):
+        raise ValueError("fused unmerge: unexpected meta layout")
+    sh = None if dst_shift is None else np.ascontiguousarray(dst_shift, dtype=I64)
+    _value_check(lib, lib.yb_tables_scatter(_ptr(um), n, gn, _ptr(md), nprob, None if sh is None else _ptr(sh)))
+    out = _fetch(lib)
+    nprob_, ng, nrow, ncol, ndst = (int(v) for v in out[:5])
+    cuts = np.cumsum([5, nprob_, ng + 1, nrow, ng + 1, ncol, ng + 1, ndst])
+    return tuple(out[cuts[k]:cuts[k + 1]] for k in range(7))
+
+
+def add_tables(metas, signs=None):
+    """Rounds of LINCOMB records of backend.add / sub (yastn/backend/backend_torch.py:518-534): ``new[sl_c] (+/-)= data_k[sl_a]``
+    for every (sl_c, sl_a) of ``metas[k]``; output ranges no operand writes stay zero.  One launch adds up to four operands;
+    with more, later rounds read the running sum as their first source.  Returns a list of (records, operand indices) —
+    operand index -1 is the output itself."""
+    n_ops = len(metas)
+    if n_ops == 0:
+        return []
+    lib = _lib.load()
+    rows = [(k, c[0], c[1], a[0]) for k, meta in enumerate(metas) for (c, a) in meta]
+    ops = np.array(rows, dtype=I64).reshape(len(rows), 4)
+    sg = np.array(signs or (1,) * n_ops, dtype=I64)
+    _value_check(lib, lib.yb_tables_add(_ptr(ops), ops.shape[0], n_ops, _ptr(sg)))
+    out = _fetch(lib)
+    rounds, pos = [], 1
+    for _ in range(int(out[0])):
+        m, ns = int(out[pos]), int(out[pos + 1])
+        slots = [int(v) for v in out[pos + 2:pos + 2 + ns]]
+        rounds.append((out[pos + 6:pos + 6 + 16 * m].reshape(m, 16), slots))
+        pos += 6 + 16 * m
+    return rounds
+
+
+# -------------------------------------------------------------------------------------------------
 # device plans
 # -------------------------------------------------------------------------------------------------
 
 def _ptr(a):
-    return a.ctypes.data_as(ctypes.c_void_p)
+    return a.ctypes.data          # plain address: every pointer argument is declared c_void_p (data_as costs 5 us per call)
 
 
 class CopyPlan:
