@@ -162,13 +162,14 @@ def test_sector_parallel_svd_many_sectors_cuda():
 @pytest.mark.parametrize("dtype", [torch.float64, torch.complex128])
 def test_batched_jacobi_svd_small_sectors_cuda(dtype):
     """Sectors up to 64 x 64 are factorised by ONE launch of the one-sided Jacobi kernel (csrc/yb_svd.cu).  Against numpy's
-    LAPACK SVD of the same data: singular values to 1e-13 * S_max (1e-14 absolute on a spectrum graded over twelve decades),
+    LAPACK SVD of the same data: singular values to 1e-13 * S_max (4e-14 absolute on a spectrum graded over twelve decades),
     reconstruction and orthogonality to 1e-13, descending order, bit-identical
     repeats; a rank-deficient sector and a zero sector are reported by the kernel and redone by the library routine."""
     rng = np.random.default_rng(2)
     shapes = [(1, 1), (1, 7), (7, 1), (2, 2), (8, 8), (17, 33), (33, 17), (64, 64), (64, 3), (3, 64), (31, 32), (50, 50), (63, 64), (5, 5), (6, 6)]
     meta, n, sizes = _svd_meta(shapes)
     fns = decomp.make(stock)
+    torch.manual_seed(11)                  # the inputs are drawn on the device: fixed, so that a failure reproduces
     data = torch.randn(n, dtype=dtype, device="cuda")
     # sector 11 (50 x 50): graded spectrum; sector 13 (5 x 5): rank 2; sector 14 (6 x 6): all zero
     sl, D = meta[11][0], meta[11][1]
@@ -200,7 +201,8 @@ def test_batched_jacobi_svd_small_sectors_cuda(dtype):
         k = s.size
         assert np.linalg.norm(u.conj().T @ u - np.eye(k)) <= 1e-13 * k and np.linalg.norm(vh @ vh.conj().T - np.eye(k)) <= 1e-13 * k, (i, DA)
     s = S[meta[11][4][0]:meta[11][4][1]].cpu().numpy()
-    assert np.abs(s - sg.cpu().numpy()).max() <= 1e-14           # the matrix itself is only defined to eps * S_max
+    # the matrix is built as Q1 diag(sg) Q2 in floating point, i.e. it is itself only defined to a few eps * S_max
+    assert np.abs(s - sg.cpu().numpy()).max() <= 4e-14
 
 
 @pytest.mark.gpu

@@ -158,11 +158,23 @@ def main():
     ap.add_argument("--shim", action="store_true", help="CPU table interpreter instead of the kernels (host-logic check, tests/cpu_shim.py)")
     ap.add_argument("--fused", action="store_true", help="b200 only: fuse dot+unmerge into one launch (yastn_backend.enable_fused_tensordot)")
     ap.add_argument("--chains", action="store_true", help="b200 only: record / replay the tensordot chains of Heff and the environment updates (yastn_b200.chain)")
+    ap.add_argument("--spmd", action="store_true", help="b200 only, under torchrun: every rank runs the same sweep, large contractions and the sectors of the "
+                    "decompositions are sharded over the ranks (yastn_b200.spmd); rank 0 prints")
+    ap.add_argument("--spmd-min-flops", type=float, default=None)
+    ap.add_argument("--gc-freeze", action="store_true", help="gc.freeze() after the model is built (keeps Python's cyclic GC off YASTN's cached metadata)")
     ap.add_argument("--decomp-workers", type=int, default=None, help="b200 only: sector streams of svd/qr/eigh (1 = the reference's serial loop)")
     ap.add_argument("--profile", action="store_true", help="time every backend function (device-synchronised: perturbs the totals)")
     ap.add_argument("--gemm-roofline", action="store_true", help="CUDA-event time and FLOP count of every dot / dot_unmerge launch (no sync inside the sweep)")
     args = ap.parse_args()
     from yastn_loader import load_yastn
+    rank, world = 0, 1
+    if args.spmd:
+        import torch
+        import torch.distributed as dist
+        rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+        if args.device != "cpu" and not args.shim:
+            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("gloo" if (args.shim or args.device == "cpu") else "nccl", rank=rank, world_size=world)
     yastn = load_yastn(allow_reference_checkout=False)
     if yastn is None:
         print(json.dumps({"unavailable": "yastn not importable: run tools/install_reference.sh"}))
@@ -185,6 +197,11 @@ def main():
         if args.chains:
             from yastn_b200 import chain
             chain.enable()
+        if args.spmd:
+            from yastn_b200 import spmd
+            if args.shim:
+                spmd._bk_usable = lambda d: True
+            spmd.enable(min_flops=args.spmd_min_flops)
     else:
         backend = args.backend
     device = "cpu" if args.backend == "np" else args.device
@@ -202,6 +219,10 @@ def main():
     if device != "cpu":
         import torch
         sync = torch.cuda.synchronize
+    if args.gc_freeze:
+        import gc
+        gc.collect()
+        gc.freeze()
     times, energies = [], []
     opts_svd = {"tol": 1e-10, "D_total": args.D}
     t_all = time.perf_counter()
@@ -215,12 +236,23 @@ def main():
     if args.backend == "b200" and args.chains:
         line["backend"] += "+chains"
         line["chains"] = chain.stats()
+    if args.spmd:
+        line["spmd"] = dict(spmd.stats(), world=world)
+        line["backend"] += f"+spmd{world}"
+        from yastn_b200 import decomp
+        line["decomp_stats"] = decomp.stats()
     if roof is not None:
         line["gemm_roofline"] = roof()
     if args.profile:
         top = sorted(prof.items(), key=lambda kv: -kv[1][1])[:14]
         line["backend_profile"] = {k: {"calls": v[0], "s": round(v[1], 3)} for k, v in top}
         line["backend_total_s"] = round(sum(v[1] for v in prof.values()), 3)
+    if args.spmd:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+        if rank != 0:
+            return
     print(json.dumps(line))
     if args.out:
         with open(args.out, "a") as f:

@@ -284,10 +284,11 @@ def _dot_unmerge_forward(Adata, Bdata, meta_dot, Dsize, meta_unmerge, out=None, 
         return {"fwd": plans.GemmPlan(problems, segments, _DTYPE_CODE[dtype], dev, scatter), "ref": (meta_unmerge, dst_shift)}
     ent = _CACHE.get(key, meta_dot, build)
     if ent["fwd"] is None:
-        res = _Unmerge.forward(_Dot.forward(Adata, Bdata, meta_dot, Dsize), meta_unmerge)
         if out is None:
-            return res
-        out.copy_(res)
+            return _Unmerge.forward(_Dot.forward(Adata, Bdata, meta_dot, Dsize), meta_unmerge)
+        # caller's buffer (a rank's share of a sharded contraction): only the records' destinations may be touched
+        tmp = _Dot.forward(Adata, Bdata, meta_dot, Dsize)
+        _run_copy(_unmerge_plans(tmp, meta_unmerge)["fwd"], tmp, out, zero=False)
         return out
     if out is None:
         out = torch.empty(Dsize, dtype=dtype, device=Adata.device)
@@ -466,6 +467,30 @@ def dot_unmerge(Adata, Bdata, meta_dot, Dsize, meta_unmerge, out=None, dst_shift
             raise ValueError("yastn_b200.dot_unmerge: out= / dst_shift= are forward-only")
         return _DotUnmerge.apply(Adata, Bdata, meta_dot, Dsize, meta_unmerge)
     return _dot_unmerge_forward(Adata, Bdata, meta_dot, Dsize, meta_unmerge, out, dst_shift)
+
+
+def dot_into(Adata, Bdata, meta_dot, out):
+    """``dot`` into the caller's buffer: only the C blocks of ``meta_dot`` are written (a rank's row panels of a sharded
+    contraction, yastn_b200.spmd).  Forward only."""
+    _check(Adata, "dot_into")
+    _check(Bdata, "dot_into")
+    Adata, Bdata, dtype = _promote(Adata, Bdata)
+    if out.dtype != dtype or out.device != Adata.device or not out.is_contiguous():
+        raise ValueError("yastn_b200.dot_into: out must be a contiguous 1-D tensor of the result's dtype and device")
+    _run_gemm(_dot_plans(meta_dot, dtype, Adata.device.index)["fwd"], Adata, Bdata, out)
+    return out
+
+
+def transpose_and_merge_partial(data, order, meta_new, meta_mrg, Dsize):
+    """``transpose_and_merge`` of a subset of the merged blocks (a rank's share of a sharded contraction): the result has the
+    full size ``Dsize`` but only the blocks of ``meta_new`` are defined — cells of those blocks that no source block covers are
+    zero-filled by the plan's own records, everything else stays uninitialised and must not be read.  Forward only."""
+    _check(data, "transpose_and_merge_partial")
+    ent = _merge_plans(data, order, meta_new, meta_mrg, Dsize)
+    out = torch.empty(Dsize, dtype=data.dtype, device=data.device)
+    kept = sum(hi - lo for (_, _, (lo, hi)) in meta_new)
+    _run_copy(ent["fwd"], data, out, zero=ent["fwd"].covered < kept)     # the zero-fill records were not built: clear everything
+    return out
 
 
 def transpose_dot_sum(Adata, Bdata, meta_dot, Areshape, Breshape, Aorder, Border, Dsize):

@@ -30,8 +30,11 @@ struct DevicePool {
     cudaEvent_t copy_done = nullptr;
     char* staging = nullptr;          // pinned host buffer of the batched table uploads
     size_t staging_bytes = 0;
+    char* slab = nullptr;             // current slab small blocks are carved from
+    size_t slab_used = 0;
 };
 constexpr size_t kStagingMax = 8u << 20;
+constexpr size_t kSlabBytes = 8u << 20;
 DevicePool& pool_of(int device) {
     static DevicePool pools[64];
     return pools[(device >= 0 && device < 64) ? device : 0];
@@ -62,6 +65,28 @@ int pool_alloc(int device, size_t bytes, void** ptr, size_t* cap) {
             p.free_blocks[c].pop_back();
             return kOk;
         }
+    }
+    // No recycled block: carve one from the current slab.  A cudaMalloc per plan costs 100-250 us and a launch-bound sweep
+    // creates thousands of plans that are never freed (profiles/host_profile_r02.txt), a slab costs one cudaMalloc per 8 MiB.
+    if (*cap <= kSlabBytes / 8) {
+        std::lock_guard<std::mutex> lk(p.mu);
+        if (!p.slab || p.slab_used + *cap > kSlabBytes) {
+            void* slab = nullptr;
+            YB_CUDA(cudaMalloc(&slab, kSlabBytes));
+            p.slab = (char*)slab;      // the rest of the previous slab is abandoned (at most one eighth of it)
+            p.slab_used = 0;
+        }
+        // blocks are powers of two >= 512 B: aligning the bump pointer to the block size keeps every block naturally aligned
+        size_t off = (p.slab_used + *cap - 1) & ~(*cap - 1);
+        if (off + *cap > kSlabBytes) {
+            void* slab = nullptr;
+            YB_CUDA(cudaMalloc(&slab, kSlabBytes));
+            p.slab = (char*)slab;
+            off = 0;
+        }
+        *ptr = p.slab + off;
+        p.slab_used = off + *cap;
+        return kOk;
     }
     YB_CUDA(cudaMalloc(ptr, *cap));
     return kOk;

@@ -96,7 +96,7 @@ def _sector_svd(A, fullrank_uv):
                 with _pools_lock:
                     _stats["svdp_sectors"] = _stats.get("svdp_sectors", 0) + 1
                 return U, S, Vh
-    return torch.linalg.svd(A, full_matrices=fullrank_uv, driver=_torch_driver())
+    return torch.linalg.svd(A, full_matrices=fullrank_uv, driver=_torch_driver() if A.is_cuda else None)
 
 
 def _pool(device):
@@ -211,6 +211,33 @@ def _jacobi_svd(data, meta, small, Udata, Sdata, Vhdata, vectors=True):
     return [small[i] for i in bad]
 
 
+# ---- several GPUs (yastn_b200.spmd): the sectors of one decomposition are dealt to the ranks, every rank factorises its share
+# into zeroed outputs and one all-reduce per output completes them everywhere (each entry is written by exactly one rank)
+_spmd = {"all_reduce": None, "rank": 0, "world": 1}
+_SPMD_MIN_COST = float(os.environ.get("YASTN_B200_SPMD_DECOMP_MIN", "5e7"))
+
+
+def set_spmd(all_reduce, rank, world):
+    _spmd.update(all_reduce=all_reduce, rank=rank, world=world)
+
+
+def _my_sectors(costs):
+    """Indices of the sectors this rank factorises (LPT on the cost, identical on every rank), or None: not sharded."""
+    if _spmd["all_reduce"] is None or _spmd["world"] < 2 or len(costs) < 2 or sum(costs) < _SPMD_MIN_COST:
+        return None
+    import heapq
+    heap = [(0, r) for r in range(_spmd["world"])]
+    mine = []
+    for i in sorted(range(len(costs)), key=lambda i: (-costs[i], i)):
+        load, r = heapq.heappop(heap)
+        if r == _spmd["rank"]:
+            mine.append(i)
+        heapq.heappush(heap, (load + costs[i], r))
+    with _pools_lock:
+        _stats["spmd_calls"] = _stats.get("spmd_calls", 0) + 1
+    return sorted(mine)
+
+
 def _svd_cost(D):
     m, n = D
     return m * n * min(m, n)
@@ -221,15 +248,17 @@ def make(stock):
     require grad or live on the CPU)."""
 
     def _defer(*tensors):
-        return any((not t.is_cuda) or (torch.is_grad_enabled() and t.requires_grad) for t in tensors)
+        return any((not (t.is_cuda or _THREADS_WITHOUT_STREAMS)) or (torch.is_grad_enabled() and t.requires_grad) for t in tensors)
 
     def svd(data, meta, sizes, fullrank_uv=False, ad_decomp_reg=1.0e-12, diagnostics=None, **kwargs):
         if _defer(data):
             return stock.svd(data, meta, sizes, fullrank_uv=fullrank_uv, ad_decomp_reg=ad_decomp_reg, diagnostics=diagnostics, **kwargs)
         real_dtype = data.real.dtype if data.is_complex() else data.dtype
-        Udata = torch.empty(sizes[0], dtype=data.dtype, device=data.device)
-        Sdata = torch.empty(sizes[1], dtype=real_dtype, device=data.device)
-        Vhdata = torch.empty(sizes[2], dtype=data.dtype, device=data.device)
+        mine = None if fullrank_uv else _my_sectors([_svd_cost(m[1]) for m in meta])
+        alloc = torch.empty if mine is None else torch.zeros
+        Udata = alloc(sizes[0], dtype=data.dtype, device=data.device)
+        Sdata = alloc(sizes[1], dtype=real_dtype, device=data.device)
+        Vhdata = alloc(sizes[2], dtype=data.dtype, device=data.device)
 
         def one(rec):
             sl, D, slU, DU, slS, slV, DV = rec
@@ -237,7 +266,7 @@ def make(stock):
             Udata[slU[0]:slU[1]].view(DU).copy_(U)
             Sdata[slS[0]:slS[1]].copy_(S)
             Vhdata[slV[0]:slV[1]].view(DV).copy_(Vh)
-        rest = list(range(len(meta)))
+        rest = list(range(len(meta))) if mine is None else mine
         if _JACOBI_MAX > 0 and not fullrank_uv and data.dtype in (torch.float64, torch.complex128):
             small = [i for i in rest if max(meta[i][1]) <= min(_JACOBI_MAX, 64) and min(meta[i][1]) >= 1]
             if small:
@@ -246,6 +275,9 @@ def make(stock):
                 rest = [i for i in rest if i not in done]
         recs = meta if len(rest) == len(meta) else [meta[i] for i in rest]
         run_sectors(one, recs, [_svd_cost(m[1]) for m in recs], data.device)
+        if mine is not None:
+            for t in (Udata, Sdata, Vhdata):
+                _spmd["all_reduce"](t)
         return Udata, Sdata, Vhdata
 
     def svdvals(data, meta, sizeS, **kwargs):
@@ -272,7 +304,12 @@ def make(stock):
             S, U = torch.linalg.eigh(data[sl[0]:sl[1]].view(D))
             Sdata[slS[0]:slS[1]].copy_(S)
             Udata[slU[0]:slU[1]].view(DU).copy_(U)
-        run_sectors(one, meta, [m[1][0] ** 3 for m in meta], data.device)
+        mine = _my_sectors([m[1][0] ** 3 for m in meta])
+        recs = meta if mine is None else [meta[i] for i in mine]
+        run_sectors(one, recs, [m[1][0] ** 3 for m in recs], data.device)
+        if mine is not None:
+            _spmd["all_reduce"](Sdata)
+            _spmd["all_reduce"](Udata)
         return Sdata, Udata
 
     def qr(data, meta, sizes):
@@ -289,7 +326,12 @@ def make(stock):
             sR[sR == 0] = 1
             Qdata[slQ[0]:slQ[1]].view(DQ).copy_(Q * sR)       # positive diagonal of R
             Rdata[slR[0]:slR[1]].view(DR).copy_(sR.reshape([-1, 1]) * R)
-        run_sectors(one, meta, [_svd_cost(m[1]) for m in meta], data.device)
+        mine = _my_sectors([_svd_cost(m[1]) for m in meta])
+        recs = meta if mine is None else [meta[i] for i in mine]
+        run_sectors(one, recs, [_svd_cost(m[1]) for m in recs], data.device)
+        if mine is not None:
+            _spmd["all_reduce"](Qdata)
+            _spmd["all_reduce"](Rdata)
         return Qdata, Rdata
 
     return {"svd": svd, "svdvals": svdvals, "eigh": eigh, "qr": qr}

@@ -1,0 +1,153 @@
+"""Sector-sharded execution of an unmodified YASTN program on several GPUs (BASELINE config 3 "sectors sharded
+over 1/2/4/8 B200").
+
+One process per GPU, every process runs the SAME YASTN program on replicated tensors (SPMD) — DMRG, CTMRG, a user's script —
+and the two kinds of work a sweep is made of are split between the ranks from metadata alone:
+
+* **contractions**: a ``fuse_to_matrix`` tensordot (yastn/tensor/_contractions.py:139-156) above ``min_flops`` is cut into
+  FLOP-balanced row panels of its charge sectors (``sharding.shard_f2m`` — a Z2 tensor has two sectors and still uses 8 GPUs).
+  A rank merges only the source blocks that fill its rows of A and the B blocks of its sectors, multiplies its panels and
+  scatters them (fused unmerge epilogue) into a zeroed result of full size; one all-reduce over NVLink/NVSwitch (NCCL, on the
+  caller's stream) then leaves the complete result on every rank.  Every element is produced by exactly one rank and summed
+  with zeros, so all ranks hold the same bits and take the same decisions afterwards (truncation, convergence tests).
+* **decompositions**: the charge sectors of ``svd`` / ``eigh`` / ``qr`` are dealt to the ranks (LPT on the sector cost),
+  factorised into zeroed outputs and all-reduced the same way (yastn_b200.decomp).
+
+Small contractions and everything else (vector operations, metadata) run replicated: they are launch-bound, an exchange would
+cost more than it saves.  The reference has no multi-GPU path for a single tensor network contraction; its only multi-process
+code farms whole CTM environments out to workers (yastn/tn/fpeps/envs/_env_ctm_dist_mp.py:117-168).
+
+    torchrun --nproc-per-node 4 my_dmrg.py        # my_dmrg.py: dist.init_process_group("nccl"); yastn_b200.spmd.enable()
+"""
+import torch
+
+from . import backend_b200 as _bk
+from . import sharding as _sh
+
+_state = {"group": None, "rank": 0, "world": 1, "min_flops": 4.0e9, "saved_f2m": None,
+          "stats": {"sharded": 0, "replicated": 0, "allreduce_bytes": 0, "sharded_flops": 0.0, "decomp_sharded": 0}}
+_plans = {}
+
+
+def active():
+    return _state["world"] > 1 and _state["saved_f2m"] is not None
+
+
+def rank_world():
+    return _state["rank"], _state["world"]
+
+
+def stats():
+    return dict(_state["stats"])
+
+
+def all_reduce_(t):
+    """Sum ``t`` over the ranks in place, on the caller's stream (complex tensors through their real view)."""
+    import torch.distributed as dist
+    buf = torch.view_as_real(t) if t.is_complex() else t
+    dist.all_reduce(buf, group=_state["group"])
+    _state["stats"]["allreduce_bytes"] += t.numel() * t.element_size()
+    return t
+
+
+def _stage_for(rank, world, order_a, mm_a, mn_a, size_a, order_b, mm_b, mn_b, size_b, meta_dot, size_m, meta_unmerge):
+    stage = {"merge_a": None if mm_a is None else {"order": order_a, "meta_new": mn_a, "meta_mrg": mm_a, "Dsize": size_a},
+             "merge_b": None if mm_b is None else {"order": order_b, "meta_new": mn_b, "meta_mrg": mm_b, "Dsize": size_b},
+             "dot": {"meta_dot": meta_dot, "Dsize": size_m},
+             "unmerge": None if meta_unmerge is None else {"meta": meta_unmerge}}
+    return _sh.shard_f2m(stage, rank, world, panels=True)
+
+
+def _merge_part(data, m):
+    """transpose_and_merge restricted to the blocks a rank needs: the destination has full size, blocks outside the rank's share
+    are neither written nor read afterwards."""
+    return _bk.transpose_and_merge_partial(data, m["order"], m["meta_new"], m["meta_mrg"], m["Dsize"])
+
+
+def enable(group=None, min_flops=None):
+    """Shard the large contractions and the decompositions of every YASTN call made from now on over the ranks of ``group``
+    (default: the world group of an initialised torch.distributed).  Every rank must run the same program."""
+    import torch.distributed as dist
+    import yastn.tensor._contractions as C
+    import yastn.tensor._merging as M
+    from . import decomp
+    if not dist.is_initialized():
+        raise RuntimeError("yastn_b200.spmd.enable: torch.distributed is not initialised")
+    _state.update(group=group, rank=dist.get_rank(group), world=dist.get_world_size(group))
+    if min_flops is not None:
+        _state["min_flops"] = float(min_flops)
+    decomp.set_spmd(all_reduce_ if _state["world"] > 1 else None, _state["rank"], _state["world"])
+    if _state["saved_f2m"] is not None or _state["world"] == 1:
+        return
+    _state["saved_f2m"] = C._tensordot_f2m
+    st = _state["stats"]
+
+    def tensordot_f2m(a, b, nout_a, nin_a, nin_b, nout_b, s_c):
+        backend = a.config.backend
+        da, db = a._data, b._data
+        native = getattr(backend, "dot_unmerge", None) is not None and da.dtype in _bk._DTYPE_CODE and da.dtype == db.dtype \
+            and _bk_usable(da) and _bk_usable(db) and not (torch.is_grad_enabled() and (da.requires_grad or db.requires_grad))
+        if not native:
+            return _state["saved_f2m"](a, b, nout_a, nin_a, nin_b, nout_b, s_c)
+        ind_a, ind_b = C._common_inds(a.struct.t, b.struct.t, nin_a, nin_b, a.ndim_n, b.ndim_n, a.config.sym.NSYM)
+        struct_a, slices_a, mm_a, ls_l, ls_ac = M._meta_merge_to_matrix(a.config, a.struct, a.slices, (nout_a, nin_a), ind_a)
+        struct_b, slices_b, mm_b, ls_bc, ls_r = M._meta_merge_to_matrix(b.config, b.struct, b.slices, (nin_b, nout_b), ind_b)
+        if ls_ac != ls_bc:
+            raise C.YastnError('Bond dimensions do not match.')
+        meta_dot, struct_m, slices_m = C._meta_tensordot_f2m(struct_a, slices_a, struct_b, slices_b)
+        key = (id(mm_a), id(mm_b), id(meta_dot), nout_a, nin_a, nin_b, nout_b, s_c, _state["rank"], _state["world"])
+        ent = _plans.get(key)
+        if ent is None or ent[0] is not mm_a or ent[1] is not mm_b or ent[2] is not meta_dot:
+            flops = sum(2.0 * Da[0] * Da[1] * Db[1] for (_, _, _, Da, _, Db) in meta_dot) * (4 if da.is_complex() else 1)
+            sharded = None
+            if flops >= _state["min_flops"]:
+                order_a, order_b = nout_a + nin_a, nin_b + nout_b
+                mn_a = tuple((x, y, z.slcs[0]) for x, y, z in zip(struct_a.t, struct_a.D, slices_a))
+                mn_b = tuple((x, y, z.slcs[0]) for x, y, z in zip(struct_b.t, struct_b.D, slices_b))
+                plain_a = ind_a is None and tuple(range(len(order_a))) == order_a and struct_a.size == len(da) \
+                    and M._no_change_in_transpose_and_merge(mm_a, mn_a, struct_a.size)
+                plain_b = ind_b is None and tuple(range(len(order_b))) == order_b and struct_b.size == len(db) \
+                    and M._no_change_in_transpose_and_merge(mm_b, mn_b, struct_b.size)
+                meta_unmerge, struct_c, slices_c = C._meta_unmerge_matrix(a.config, struct_m, slices_m, ls_l, ls_r, s_c)
+                plain_c = M._no_change_in_unmerge(meta_unmerge)
+                stage, _ = _stage_for(_state["rank"], _state["world"], order_a, None if plain_a else mm_a, mn_a, struct_a.size,
+                                      order_b, None if plain_b else mm_b, mn_b, struct_b.size, meta_dot, struct_m.size,
+                                      None if plain_c else meta_unmerge)
+                sharded = (stage, struct_c, slices_c, flops)
+            if len(_plans) > 4096:
+                _plans.clear()
+            ent = (mm_a, mm_b, meta_dot, sharded)
+            _plans[key] = ent
+        if ent[3] is None:
+            st["replicated"] += 1
+            return _state["saved_f2m"](a, b, nout_a, nin_a, nin_b, nout_b, s_c)
+        stage, struct_c, slices_c, flops = ent[3]
+        if _bk._recorder is not None:
+            _bk._recorder.unsupported("collective")      # a chain must never replay this without its all-reduce
+        data_a = da if stage["merge_a"] is None else _merge_part(da, stage["merge_a"])
+        data_b = db if stage["merge_b"] is None else _merge_part(db, stage["merge_b"])
+        out = torch.zeros(struct_m.size, dtype=da.dtype, device=da.device)
+        if stage["unmerge"] is None:
+            _bk.dot_into(data_a, data_b, stage["dot"]["meta_dot"], out)
+        else:
+            _bk.dot_unmerge(data_a, data_b, stage["dot"]["meta_dot"], struct_m.size, stage["unmerge"]["meta"], out=out)
+        all_reduce_(out)
+        st["sharded"] += 1
+        st["sharded_flops"] += flops
+        return out, struct_c, slices_c
+    C._tensordot_f2m = tensordot_f2m
+
+
+def _bk_usable(d):
+    return d.is_cuda
+
+
+def disable():
+    from . import decomp
+    decomp.set_spmd(None, 0, 1)
+    if _state["saved_f2m"] is not None:
+        import yastn.tensor._contractions as C
+        C._tensordot_f2m = _state["saved_f2m"]
+        _state["saved_f2m"] = None
+    _state.update(group=None, rank=0, world=1)
+    _plans.clear()
