@@ -280,6 +280,26 @@ def gpu_baseline(sizes, cplx, dev, flops):
     return out
 
 
+def dmrg_sweep_spmd(rank, world, timeout=900):
+    """The same DMRG sweep run SPMD on all ranks of this job (yastn_b200.spmd: contractions sharded by row panels, SVD sectors
+    dealt to the ranks, results completed by NCCL all-reduces over NVLink).  Every bench rank starts one child rank (fresh
+    process, own rendezvous port); rank 0 returns the child's line."""
+    env = dict(os.environ)
+    env["MASTER_PORT"] = str(int(env.get("MASTER_PORT", "29500")) + 23)
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "dmrg_bench.py"), "--model", "hubbard", "--N", "20", "--D", "4096", "--D0", "4096",
+           "--sweeps", "1", "--dtype", "complex128", "--backend", "b200", "--fused", "--spmd"]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+        if rank != 0:
+            return None
+        d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+        return {"sweep_s": d["sweep_s"][0], "energy": d["energy"][0], "ranks": world, "spmd": d.get("spmd"), "decomp": d.get("decomp_stats"),
+                "config": "U(1)xU(1) Hubbard N=20, 2-site DMRG, D=4096, complex128, one sweep; every rank runs the unmodified yastn program, "
+                          "tensordots above 4 GFLOP sharded by row panels + all-reduce, SVD sectors sharded + all-reduce"}
+    except Exception as e:
+        return {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"} if rank == 0 else None
+
+
 def dmrg_sweep(which, timeout=900):
     """One 2-site DMRG sweep, U(1)xU(1) Hubbard N=20 D=4096 complex128, in a fresh process (tools/dmrg_bench.py)."""
     cmd = [sys.executable, os.path.join(ROOT, "tools", "dmrg_bench.py"), "--model", "hubbard", "--N", "20", "--D", "4096", "--D0", "4096",
@@ -552,6 +572,15 @@ def main():
         e2e = {"value": total_flops / (e2e_max * 1e-3) * 1e-9, "unit": "GFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": e2e_max}
 
+    spmd_dmrg = None
+    if world > 1 and not args.no_dmrg:
+        # second workload at N > 1: a whole DMRG sweep on all ranks, with the NCCL exchange inside the timed sweep
+        del work, operands
+        if not args.no_e2e:
+            del host_ops, out_host
+        torch.cuda.empty_cache()
+        barrier()
+        spmd_dmrg = dmrg_sweep_spmd(rank, world)
     if rank == 0:
         # DRAM bytes of the dominant launch from the committed ncu --set full capture (not measurable outside a profiler)
         traffic = traffic_of = None
@@ -590,6 +619,8 @@ def main():
                 "clocks": clocks}
         if e2e is not None:
             line["e2e"] = e2e
+        if spmd_dmrg is not None:
+            line["spmd_dmrg_sweep"] = spmd_dmrg
         if world == 1:
             del work, operands
             torch.cuda.empty_cache()

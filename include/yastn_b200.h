@@ -16,8 +16,8 @@
  *   yb_gemm_*  : backend.dot                  yastn/backend/backend_torch.py:549 (loop: _backend_torch_backwards.py:100-109, backward 118-138)
  *                backend.transpose_dot_sum    yastn/backend/backend_torch.py:553 (loop: _backend_torch_backwards.py:143-157)
  *                prior art: experimental/torch_mmib.cpp:20-35 ("mm incommensurate batch")
- *   yb_match_* : pairing of charge sectors    yastn/tensor/_contractions.py:281-298 (_meta_tensordot_f2m), 250-278 (_common_inds);
- *                single-call boundary         yastn/backend/backend_torch_cpp.py:173-228 (kernel_tensordot_bs)
+ *   yb_tables_*: the meta pass between the reference's meta tuples and the plan tables (host code, yb_tables.cu)
+ *   yb_chain_* : several tensordots in a row (Heff2, environment updates; yastn/tn/mps/_env.py:496-518) as one call
  */
 #ifndef YASTN_B200_H
 #define YASTN_B200_H
@@ -147,20 +147,6 @@ int yb_svd_plan_create(const int64_t* recs, int64_t nrec, int itemsize, int devi
 int yb_svd_run(const yb_svd_plan* plan, const void* A, void* U, void* S, void* Vh, void* status, int max_sweeps, int vectors,
                void* stream);
 void yb_svd_plan_destroy(yb_svd_plan* plan);
-
-/* ------------------------------------------------------------------------------------------------
- * Device-side sector matching (meta pass).  All pointers are DEVICE pointers.  A blocks (table order = the reference's
- * block order, outgoing charges first) are joined with B blocks (sorted by contracted charge first) on the contracted
- * charge a_key / b_key ([n, key_width] int64); a_dims = [na, 2] (M, K), b_dims = [nb, 2] (K, N), *_off = block offsets.
- * Writes, in the order of the reference's meta_dot (yastn/tensor/_contractions.py:281-346), one problem row
- * [M, N, offC, ldc, seg, seg+1] and one segment row [K, offA, K, 1, offB, N, 1] per matching pair — the tables of
- * yb_gemm_plan_create — and result = [pairs, C elements, status] (status 1: contracted dimensions differ, 2: more than
- * `capacity` pairs).  scratch needs yb_match_scratch_elems(na, nb) int64.
- * ---------------------------------------------------------------------------------------------- */
-int64_t yb_match_scratch_elems(int64_t na, int64_t nb);
-int yb_match_sectors(const int64_t* a_key, const int64_t* a_dims, const int64_t* a_off, int64_t na,
-                     const int64_t* b_key, const int64_t* b_dims, const int64_t* b_off, int64_t nb, int key_width,
-                     int64_t capacity, int64_t* problems, int64_t* segments, int64_t* result, int64_t* scratch, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Host-side meta pass (no device calls): the reference's meta tuples, flattened depth-first to int64 tables, become the

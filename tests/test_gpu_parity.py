@@ -427,37 +427,6 @@ def test_gemm_tall_and_skinny_problems(bk):
         assert _relerr(gA.grad.cpu().numpy(), ra) <= TOL and _relerr(gB.grad.cpu().numpy(), rb) <= TOL
 
 
-def test_device_sector_matching_bit_exact():
-    """yb_match_sectors (device join + scans) reproduces the reference's meta_dot for every recorded benchmark structure,
-    fuse_to_matrix and fuse_contracted, bit-exactly; the GEMM run from the device-built tables equals backend.dot."""
-    from yastn_b200 import sectors, plans as _plans, backend_b200 as bk_
-    checked = 0
-    for name, case in bench_structs().items():
-        nsym = case["a"]["nsym"]
-        for pol, tables in (("f2m", sectors.block_tables_f2m), ("fc", sectors.block_tables_fc)):
-            st = case.get(pol)
-            if st is None or st["merge_a"] is None or st["merge_b"] is None:
-                continue
-            ba = tuple((tn, Dn, sln) for tn, Dn, sln in st["merge_a"]["meta_new"])
-            bb = tuple((tn, Dn, sln) for tn, Dn, sln in st["merge_b"]["meta_new"])
-            problems, segments, csize = sectors.match_sectors(*tables(ba, bb, nsym), device=0)
-            assert sectors.meta_dot_from_tables(problems, segments) == st["dot"]["meta_dot"], (name, pol)
-            assert csize == st["dot"]["Dsize"]
-            p_ref, s_ref = _plans.dot_tables(st["dot"]["meta_dot"])
-            assert np.array_equal(problems, p_ref) and np.array_equal(segments, s_ref)
-            checked += 1
-    assert checked >= 10
-    # mismatching contracted dimensions are reported like the reference's 'Bond dimensions do not match.'
-    a = (((0, 0), (2, 3), (0, 6)),)
-    b = (((0, 0), (4, 5), (0, 20)),)
-    with pytest.raises(ValueError, match="Bond dimensions"):
-        sectors.match_sectors(*sectors.block_tables_f2m(a, b, 1), device=0)
-    # empty operands
-    e = np.zeros((0, 1), dtype=np.int64), np.zeros((0, 2), dtype=np.int64), np.zeros(0, dtype=np.int64)
-    problems, segments, csize = sectors.match_sectors(*e, *e, device=0)
-    assert problems.shape == (0, 6) and csize == 0
-
-
 @pytest.mark.parametrize("name", ["U1_D1024_P1", "U1_D2048_P3", "U1_D4096_T1"])
 def test_cuda_graph_capture_and_replay(bk, name):
     """The run calls allocate nothing and never synchronise (include/yastn_b200.h): a whole tensordot — merges (copy and tiled

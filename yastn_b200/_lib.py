@@ -45,8 +45,6 @@ SIGNATURES = {
     "yb_peer_open": (_c.c_int, [_vp, _c.c_int, _c.POINTER(_vp)]),
     "yb_peer_close": (_c.c_int, [_vp]),
     "yb_peer_free": (_c.c_int, [_vp]),
-    "yb_match_scratch_elems": (_c.c_int64, [_c.c_int64, _c.c_int64]),
-    "yb_match_sectors": (_c.c_int, [_vp, _vp, _vp, _c.c_int64, _vp, _vp, _vp, _c.c_int64, _c.c_int, _c.c_int64, _vp, _vp, _vp, _vp, _vp]),
 }
 
 ABI_VERSION = 4
