@@ -32,9 +32,10 @@ struct DevicePool {
     size_t staging_bytes = 0;
     char* slab = nullptr;             // current slab small blocks are carved from
     size_t slab_used = 0;
+    size_t pending_bytes = 0;
 };
-constexpr size_t kStagingMax = 8u << 20;
-constexpr size_t kSlabBytes = 8u << 20;
+constexpr size_t kStagingMax = 64u << 20;
+constexpr size_t kSlabBytes = 64u << 20;    // blocks up to 8 MiB are carved from slabs
 DevicePool& pool_of(int device) {
     static DevicePool pools[64];
     return pools[(device >= 0 && device < 64) ? device : 0];
@@ -46,56 +47,82 @@ int size_class(size_t bytes) {
 }
 }  // namespace
 
+namespace {
+// Blocks released by destroyed plans may still be read by queued kernels: they wait in `pending` until a device-wide
+// synchronisation has happened.  That synchronisation stalls the caller's pipeline, so it is only paid when a lot of memory is
+// waiting (or the device is out of memory) — never just because one plan was evicted from a cache.
+constexpr size_t kRecycleBytes = 512u << 20;
+
+int recycle_pending(DevicePool& p) {     // p.mu held
+    YB_CUDA(cudaDeviceSynchronize());
+    for (int k = 0; k < 48; ++k) {
+        p.free_blocks[k].insert(p.free_blocks[k].end(), p.pending[k].begin(), p.pending[k].end());
+        p.pending[k].clear();
+    }
+    p.pending_bytes = 0;
+    return kOk;
+}
+
+cudaError_t new_slab(DevicePool& p) {    // p.mu held; the rest of the previous slab is abandoned (less than one block)
+    void* slab = nullptr;
+    cudaError_t err = cudaMalloc(&slab, kSlabBytes);
+    if (err != cudaSuccess) return err;
+    p.slab = (char*)slab;
+    p.slab_used = 0;
+    return cudaSuccess;
+}
+}  // namespace
+
 int pool_alloc(int device, size_t bytes, void** ptr, size_t* cap) {
     DevicePool& p = pool_of(device);
     const int c = size_class(bytes);
     *cap = (size_t)1 << c;
-    {
-        std::lock_guard<std::mutex> lk(p.mu);
-        if (p.free_blocks[c].empty() && !p.pending[c].empty()) {
-            // recycle: one device-wide sync makes every block released so far safe to overwrite
-            YB_CUDA(cudaDeviceSynchronize());
-            for (int k = 0; k < 48; ++k) {
-                p.free_blocks[k].insert(p.free_blocks[k].end(), p.pending[k].begin(), p.pending[k].end());
-                p.pending[k].clear();
-            }
+    std::lock_guard<std::mutex> lk(p.mu);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        if (p.free_blocks[c].empty() && !p.pending[c].empty() && (p.pending_bytes >= kRecycleBytes || attempt == 1)) {
+            int rc = recycle_pending(p);
+            if (rc != kOk) return rc;
         }
         if (!p.free_blocks[c].empty()) {
             *ptr = p.free_blocks[c].back();
             p.free_blocks[c].pop_back();
             return kOk;
         }
-    }
-    // No recycled block: carve one from the current slab.  A cudaMalloc per plan costs 100-250 us and a launch-bound sweep
-    // creates thousands of plans that are never freed (profiles/host_profile_r02.txt), a slab costs one cudaMalloc per 8 MiB.
-    if (*cap <= kSlabBytes / 8) {
-        std::lock_guard<std::mutex> lk(p.mu);
-        if (!p.slab || p.slab_used + *cap > kSlabBytes) {
-            void* slab = nullptr;
-            YB_CUDA(cudaMalloc(&slab, kSlabBytes));
-            p.slab = (char*)slab;      // the rest of the previous slab is abandoned (at most one eighth of it)
-            p.slab_used = 0;
+        // No recycled block: carve one from the current slab.  A cudaMalloc per plan costs 100-250 us (and more for the MiB-sized
+        // tables of a D = 4096 structure); a sweep creates thousands of plans that live as long as the plan cache
+        // (profiles/host_profile_r02.txt).  A slab costs one cudaMalloc per 64 MiB.
+        cudaError_t err = cudaSuccess;
+        if (*cap <= kSlabBytes / 8) {
+            // blocks are powers of two >= 512 B: aligning the bump pointer to the block size keeps every block naturally aligned
+            size_t off = p.slab ? ((p.slab_used + *cap - 1) & ~(*cap - 1)) : kSlabBytes;
+            if (off + *cap > kSlabBytes) {
+                err = new_slab(p);
+                off = 0;
+            }
+            if (err == cudaSuccess) {
+                *ptr = p.slab + off;
+                p.slab_used = off + *cap;
+                return kOk;
+            }
+        } else {
+            err = cudaMalloc(ptr, *cap);
+            if (err == cudaSuccess) return kOk;
         }
-        // blocks are powers of two >= 512 B: aligning the bump pointer to the block size keeps every block naturally aligned
-        size_t off = (p.slab_used + *cap - 1) & ~(*cap - 1);
-        if (off + *cap > kSlabBytes) {
-            void* slab = nullptr;
-            YB_CUDA(cudaMalloc(&slab, kSlabBytes));
-            p.slab = (char*)slab;
-            off = 0;
-        }
-        *ptr = p.slab + off;
-        p.slab_used = off + *cap;
-        return kOk;
+        cudaGetLastError();
+        if (attempt == 1 || p.pending_bytes == 0)
+            return fail(kErrCuda, "yastn_b200: device allocation of %zu bytes for plan tables failed: %s", *cap, cudaGetErrorString(err));
+        // out of memory with blocks waiting: synchronise, recycle everything and try once more
+        int rc = recycle_pending(p);
+        if (rc != kOk) return rc;
     }
-    YB_CUDA(cudaMalloc(ptr, *cap));
-    return kOk;
+    return fail(kErrCuda, "yastn_b200: device allocation of %zu bytes for plan tables failed", *cap);
 }
 
 void pool_free(int device, void* ptr, size_t cap) {
     DevicePool& p = pool_of(device);
     std::lock_guard<std::mutex> lk(p.mu);
     p.pending[size_class(cap)].push_back(ptr);
+    p.pending_bytes += cap;
 }
 
 int pool_upload(int device, void* dst, const void* host, size_t bytes) {
