@@ -158,6 +158,33 @@ def test_traces_with_foreign_operations_are_never_replayed(device):
     assert chain.stats()["bypassed"] == s1["bypassed"] + 1
 
 
+def test_operands_sharing_data_are_part_of_the_key(device):
+    """<psi|H|psi> passes the same tensor as bra and ket; a later call with two different tensors of the same structure (a
+    compression environment) must not replay that recording with the ket read from the bra's buffer."""
+    psi, H = _model(device, "U1", "float64", 6)
+    psi.canonize_(to="first")
+    env = mps.Env(psi, [H, psi.shallow_copy()])          # the copy shares its tensors with psi: bra.A[n] is ket.A[n]
+    env.setup_(to="first")
+    vecL, A, W = env.F[-1, 0], psi.A[0], H.A[0]
+    other = A * 1.0
+    other._data.mul_(torch.arange(1, other._data.numel() + 1, dtype=other._data.dtype, device=other._data.device))
+    plain_same = env.update_env_to_last(vecL, 0)
+    env.ket.A[0] = other
+    plain_diff = env.update_env_to_last(vecL, 0)
+    assert not np.array_equal(_bits(plain_same), _bits(plain_diff))
+    chain.enable()
+    chain.clear()
+    env.ket.A[0] = A
+    for _ in range(2):
+        assert np.array_equal(_bits(env.update_env_to_last(vecL, 0)), _bits(plain_same))
+    env.ket.A[0] = other
+    for _ in range(2):
+        assert np.array_equal(_bits(env.update_env_to_last(vecL, 0)), _bits(plain_diff))
+    env.ket.A[0] = A
+    assert np.array_equal(_bits(env.update_env_to_last(vecL, 0)), _bits(plain_same))
+    assert chain.stats()["chains"] == 2
+
+
 def test_chain_abi_rejects_malformed_steps():
     lib = _lib.load()
     h = ctypes.c_void_p()

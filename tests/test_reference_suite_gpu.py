@@ -25,11 +25,11 @@ FULL = ["tensor/test_tensordot.py", "tensor/test_ncon_einsum.py", "tensor/test_f
 CONTRACTIONS = ["tensor/test_tensordot.py", "tensor/test_ncon_einsum.py", "tensor/test_fuse_hard.py", "tensor/test_vdot.py"]
 
 
-def _run(policy, files):
+def _run(policy, files, extra=()):
     if not os.path.isdir(REF_TESTS):
         pytest.skip("baseline/_ref/ref_tests missing (tools/install_reference.sh was not run in the authoring container)")
     files = [f for f in files if os.path.exists(os.path.join(REF_TESTS, f))]
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "run_reference_tests.py"), "--policies", policy, "--files"] + files,
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "run_reference_tests.py"), "--policies", policy, *extra, "--files"] + files,
                        capture_output=True, text=True, timeout=2400)
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
     assert lines, r.stdout[-3000:] + r.stderr[-3000:]
@@ -52,3 +52,13 @@ def test_reference_contraction_tests_other_policies(policy):
     assert d["passed"] >= 40
     native = d["hot_calls"]["native"]
     assert (native["transpose_dot_sum"] if policy == "no_fusion" else native["dot"]) > 1000
+
+
+def test_reference_mps_tests_with_recorded_chains():
+    """The reference's DMRG / TDVP / environment tests with Heff1, Heff2 and the environment updates replayed from recorded chains
+    (yastn_b200.chain) and dot + unmerge fused: no failures, and the chains really replay."""
+    d, _ = _run("fuse_to_matrix", ["mps/test_dmrg.py", "mps/test_tdvp.py", "mps/test_env.py", "mps/test_environment.py", "mps/test_measurement.py"],
+                extra=("--chains",))
+    assert d["failed"] == 0, d["failed_ids"]
+    assert d["passed"] >= 10
+    assert d["chains"]["replayed"] > d["chains"]["recorded"] > 0

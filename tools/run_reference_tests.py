@@ -44,6 +44,7 @@ def main():
     ap.add_argument("--shim", action="store_true")
     ap.add_argument("--out", default=None)
     ap.add_argument("-k", default=None)
+    ap.add_argument("--chains", action="store_true", help="also enable the fused tensordot and the recorded tensordot chains (yastn_b200.chain)")
     args = ap.parse_args()
     import pytest
     from yastn_loader import load_yastn
@@ -59,6 +60,10 @@ def main():
         cpu_shim.install()
         device = "cpu"
     yastn_backend.activate()
+    if args.chains:
+        from yastn_b200 import chain
+        yastn_backend.enable_fused_tensordot()
+        chain.enable()
     lines = []
     for policy in args.policies:
         before = yastn_backend.call_counts()
@@ -71,6 +76,8 @@ def main():
         after = yastn_backend.call_counts()
         delta = {kind: {k: after[kind][k] - before[kind][k] for k in after[kind]} for kind in after}
         line = {"policy": policy, "device": device, "rc": int(rc), **tally.c, "failed_ids": tally.failed[:20], "hot_calls": delta, "files": args.files}
+        if args.chains:
+            line["chains"] = chain.stats()
         print(json.dumps(line), flush=True)
         lines.append(line)
     if args.out:

@@ -212,7 +212,16 @@ def trace(name, fn, tensors):
     if not native:
         _stats["bypassed"] += 1
         return fn(*tensors)
-    key = (name, tensors[0].config, d0.device.index) + tuple(_sig(t) for t in tensors)
+    # operands that share their data (bra is ket in an expectation value) are one buffer to the recorder: the chain is only
+    # valid for calls with the same sharing pattern, so the pattern is part of the key; partial overlaps are never chained
+    spans = [_span(d) for d in datas]
+    alias = tuple(next(j for j in range(i + 1) if spans[j] == spans[i]) for i in range(len(spans)))
+    for i in range(len(spans)):
+        for j in range(i):
+            if alias[i] != alias[j] and spans[i][0] < spans[j][1] and spans[j][0] < spans[i][1]:
+                _stats["bypassed"] += 1
+                return fn(*tensors)
+    key = (name, tensors[0].config, d0.device.index, alias) + tuple(_sig(t) for t in tensors)
     ch = _cache.get(key, False)
     if ch is None:               # known not to be replayable
         return fn(*tensors)
