@@ -143,6 +143,28 @@ def gemm_roofline(backend, cplx_hint):
     return mod, report
 
 
+def device_is_cuda(args):
+    return args.device != "cpu" and not args.shim
+
+
+def time_f2m(prof):
+    """Device-synchronised time of every fuse_to_matrix tensordot (whatever implementation is installed: stock, fused, sharded)."""
+    import torch
+    import yastn.tensor._contractions as C
+    inner = C._tensordot_f2m
+
+    def timed(*a, **k):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = inner(*a, **k)
+        torch.cuda.synchronize()
+        e = prof.setdefault("tensordot_f2m (whole call)", [0, 0.0])
+        e[0] += 1
+        e[1] += time.perf_counter() - t0
+        return out
+    C._tensordot_f2m = timed
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--model", default="heisenberg")
@@ -202,6 +224,13 @@ def main():
             if args.shim:
                 spmd._bk_usable = lambda d: True
             spmd.enable(min_flops=args.spmd_min_flops)
+            spmd.set_profile(args.profile)
+            if device_is_cuda(args):
+                import torch.distributed as dist
+                warm = torch.zeros(1 << 20, dtype=torch.float64, device="cuda")
+                for _ in range(3):                       # NCCL builds its communicator on the first collective: not part of a sweep
+                    dist.all_reduce(warm)
+                torch.cuda.synchronize()
     else:
         backend = args.backend
     device = "cpu" if args.backend == "np" else args.device
@@ -211,6 +240,8 @@ def main():
         backend, roof = gemm_roofline(backend, args.dtype == "complex128")
     if args.profile:
         backend = profiled(backend, device, prof)
+        if device != "cpu":
+            time_f2m(prof)
     cfg_kw = dict(backend=backend, default_device=device, tensordot_policy=args.policy, default_dtype=args.dtype)
     ops, I, H, n_total = build(args.model, args.N, cfg_kw, yastn, mps)
     ops.random_seed(seed=0)

@@ -6,10 +6,12 @@ and the two kinds of work a sweep is made of are split between the ranks from me
 
 * **contractions**: a ``fuse_to_matrix`` tensordot (yastn/tensor/_contractions.py:139-156) above ``min_flops`` is cut into
   FLOP-balanced row panels of its charge sectors (``sharding.shard_f2m`` — a Z2 tensor has two sectors and still uses 8 GPUs).
-  A rank merges only the source blocks that fill its rows of A and the B blocks of its sectors, multiplies its panels and
-  scatters them (fused unmerge epilogue) into a zeroed result of full size; one all-reduce over NVLink/NVSwitch (NCCL, on the
-  caller's stream) then leaves the complete result on every rank.  Every element is produced by exactly one rank and summed
-  with zeros, so all ranks hold the same bits and take the same decisions afterwards (truncation, convergence tests).
+  A rank merges only the source blocks that fill its rows of A and the B blocks of its sectors and multiplies its panels into
+  the merged result.  The panels of a rank are ONE contiguous range of that 1-D result, so completing it on every rank is one
+  broadcast per rank over NVLink/NVSwitch (NCCL, on the caller's stream; pure copies — an all-reduce of a zero-padded result
+  was measured 4x slower because NCCL's float64 sum runs at 160 GB/s) followed by the local unmerge.  Every element is
+  produced by exactly one rank, so all ranks hold the same bits and take the same decisions afterwards (truncation,
+  convergence tests).
 * **decompositions**: the charge sectors of ``svd`` / ``eigh`` / ``qr`` are dealt to the ranks (LPT on the sector cost),
   factorised into zeroed outputs and all-reduced the same way (yastn_b200.decomp).
 
@@ -24,8 +26,8 @@ import torch
 from . import backend_b200 as _bk
 from . import sharding as _sh
 
-_state = {"group": None, "rank": 0, "world": 1, "min_flops": 4.0e9, "saved_f2m": None,
-          "stats": {"sharded": 0, "replicated": 0, "allreduce_bytes": 0, "sharded_flops": 0.0, "decomp_sharded": 0}}
+_state = {"group": None, "rank": 0, "world": 1, "min_flops": 4.0e9, "saved_f2m": None, "profile": False,
+          "stats": {"sharded": 0, "replicated": 0, "allreduce_bytes": 0, "sharded_flops": 0.0, "sharded_s": 0.0, "allreduce_s": 0.0}}
 _plans = {}
 
 
@@ -41,12 +43,48 @@ def stats():
     return dict(_state["stats"])
 
 
+def set_profile(on):
+    """Device-synchronised timing of the sharded contractions and of the all-reduces into ``stats()`` (perturbs the totals)."""
+    _state["profile"] = bool(on)
+
+
 def all_reduce_(t):
     """Sum ``t`` over the ranks in place, on the caller's stream (complex tensors through their real view)."""
+    import time
     import torch.distributed as dist
     buf = torch.view_as_real(t) if t.is_complex() else t
-    dist.all_reduce(buf, group=_state["group"])
+    if _state["profile"] and t.is_cuda:
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        dist.all_reduce(buf, group=_state["group"])
+        torch.cuda.synchronize()
+        _state["stats"]["allreduce_s"] += time.perf_counter() - t0
+    else:
+        dist.all_reduce(buf, group=_state["group"])
     _state["stats"]["allreduce_bytes"] += t.numel() * t.element_size()
+    return t
+
+
+def exchange_(t, runs):
+    """Complete ``t`` on every rank: ``runs[r]`` are the contiguous element ranges rank ``r`` has computed; each is broadcast from
+    its owner (pure copies over NVLink on the caller's stream — no reduction, so every rank ends with the same bits)."""
+    import time
+    import torch.distributed as dist
+    prof = _state["profile"] and t.is_cuda
+    if prof:
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+    flat = torch.view_as_real(t).reshape(-1) if t.is_complex() else t
+    k = 2 if t.is_complex() else 1
+    group = _state["group"]
+    for r, rr in enumerate(runs):
+        src = r if group is None else dist.get_global_rank(group, r)
+        for lo, hi in rr:
+            dist.broadcast(flat[k * lo:k * hi], src=src, group=group)
+            _state["stats"]["allreduce_bytes"] += (hi - lo) * t.element_size()
+    if prof:
+        torch.cuda.synchronize()
+        _state["stats"]["allreduce_s"] += time.perf_counter() - t0
     return t
 
 
@@ -110,10 +148,23 @@ def enable(group=None, min_flops=None):
                     and M._no_change_in_transpose_and_merge(mm_b, mn_b, struct_b.size)
                 meta_unmerge, struct_c, slices_c = C._meta_unmerge_matrix(a.config, struct_m, slices_m, ls_l, ls_r, s_c)
                 plain_c = M._no_change_in_unmerge(meta_unmerge)
+                # the unmerge is NOT sharded: a rank's row panels are one contiguous range of the merged result (`merged`), which every
+                # rank can receive with a plain broadcast; cutting the result into the output blocks is then a local copy
                 stage, _ = _stage_for(_state["rank"], _state["world"], order_a, None if plain_a else mm_a, mn_a, struct_a.size,
-                                      order_b, None if plain_b else mm_b, mn_b, struct_b.size, meta_dot, struct_m.size,
-                                      None if plain_c else meta_unmerge)
-                sharded = (stage, struct_c, slices_c, flops)
+                                      order_b, None if plain_b else mm_b, mn_b, struct_b.size, meta_dot, struct_m.size, None)
+                runs = []
+                for units in _sh.partition_rows(meta_dot, _state["world"]):
+                    spans = sorted((meta_dot[p][0][0] + r0 * meta_dot[p][5][1], meta_dot[p][0][0] + r1 * meta_dot[p][5][1]) for p, r0, r1 in units)
+                    merged = []
+                    for lo, hi in spans:
+                        if hi <= lo:
+                            continue
+                        if merged and merged[-1][1] == lo:
+                            merged[-1][1] = hi
+                        else:
+                            merged.append([lo, hi])
+                    runs.append(tuple((lo, hi) for lo, hi in merged))
+                sharded = (stage, struct_c, slices_c, flops, None if plain_c else meta_unmerge, tuple(runs))
             if len(_plans) > 4096:
                 _plans.clear()
             ent = (mm_a, mm_b, meta_dot, sharded)
@@ -121,17 +172,22 @@ def enable(group=None, min_flops=None):
         if ent[3] is None:
             st["replicated"] += 1
             return _state["saved_f2m"](a, b, nout_a, nin_a, nin_b, nout_b, s_c)
-        stage, struct_c, slices_c, flops = ent[3]
+        stage, struct_c, slices_c, flops, meta_unmerge, runs = ent[3]
+        if _state["profile"] and da.is_cuda:
+            import time
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
         if _bk._recorder is not None:
-            _bk._recorder.unsupported("collective")      # a chain must never replay this without its all-reduce
+            _bk._recorder.unsupported("collective")      # a chain must never replay this without its exchange
         data_a = da if stage["merge_a"] is None else _merge_part(da, stage["merge_a"])
         data_b = db if stage["merge_b"] is None else _merge_part(db, stage["merge_b"])
-        out = torch.zeros(struct_m.size, dtype=da.dtype, device=da.device)
-        if stage["unmerge"] is None:
-            _bk.dot_into(data_a, data_b, stage["dot"]["meta_dot"], out)
-        else:
-            _bk.dot_unmerge(data_a, data_b, stage["dot"]["meta_dot"], struct_m.size, stage["unmerge"]["meta"], out=out)
-        all_reduce_(out)
+        merged = torch.empty(struct_m.size, dtype=da.dtype, device=da.device)
+        _bk.dot_into(data_a, data_b, stage["dot"]["meta_dot"], merged)
+        exchange_(merged, runs)
+        out = merged if meta_unmerge is None else backend.unmerge(merged, meta_unmerge)
+        if _state["profile"] and da.is_cuda:
+            torch.cuda.synchronize()
+            st["sharded_s"] += time.perf_counter() - t0
         st["sharded"] += 1
         st["sharded_flops"] += flops
         return out, struct_c, slices_c
