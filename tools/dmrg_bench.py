@@ -183,6 +183,7 @@ def main():
     ap.add_argument("--spmd", action="store_true", help="b200 only, under torchrun: every rank runs the same sweep, large contractions and the sectors of the "
                     "decompositions are sharded over the ranks (yastn_b200.spmd); rank 0 prints")
     ap.add_argument("--spmd-min-flops", type=float, default=None)
+    ap.add_argument("--spmd-nccl", action="store_true", help="exchange the result panels with NCCL broadcasts instead of peer-memory stores")
     ap.add_argument("--gc-freeze", action="store_true", help="gc.freeze() after the model is built (keeps Python's cyclic GC off YASTN's cached metadata)")
     ap.add_argument("--decomp-workers", type=int, default=None, help="b200 only: sector streams of svd/qr/eigh (1 = the reference's serial loop)")
     ap.add_argument("--profile", action="store_true", help="time every backend function (device-synchronised: perturbs the totals)")
@@ -223,7 +224,7 @@ def main():
             from yastn_b200 import spmd
             if args.shim:
                 spmd._bk_usable = lambda d: True
-            spmd.enable(min_flops=args.spmd_min_flops)
+            spmd.enable(min_flops=args.spmd_min_flops, peer_arena=not args.spmd_nccl)
             spmd.set_profile(args.profile)
             if device_is_cuda(args):
                 import torch.distributed as dist

@@ -29,6 +29,7 @@ from . import sharding as _sh
 _state = {"group": None, "rank": 0, "world": 1, "min_flops": 4.0e9, "saved_f2m": None, "profile": False,
           "stats": {"sharded": 0, "replicated": 0, "allreduce_bytes": 0, "sharded_flops": 0.0, "sharded_s": 0.0, "allreduce_s": 0.0}}
 _plans = {}
+_arena = {"arena": None, "slot_bytes": 0, "next": 0, "disabled": False}      # two result slots in peer-mapped memory (double buffer)
 
 
 def active():
@@ -88,6 +89,73 @@ def exchange_(t, runs):
     return t
 
 
+def _arena_slot(nbytes, device):
+    """A result slot of at least ``nbytes`` in this rank's peer arena (every rank makes the same calls in the same order, so the
+    slots sit at the same offsets everywhere).  Two slots alternate: a peer may already push the panels of the next contraction
+    while this rank still unmerges the previous one.  Growing the arena is collective."""
+    from . import peer
+    a = _arena
+    if a["arena"] is None or a["slot_bytes"] < nbytes:
+        if a["arena"] is not None:
+            a["arena"].close()
+        slot = max(int(nbytes * 1.25), 256 << 20)
+        slot = (slot + 4095) // 4096 * 4096
+        a["arena"] = peer.PeerArena(2 * slot, device=device, group=_state["group"])
+        a["slot_bytes"], a["next"] = slot, 0
+        _plans_push.clear()
+    k = a["next"]
+    a["next"] ^= 1
+    return a["arena"], k, k * a["slot_bytes"]
+
+
+_plans_push = {}
+
+
+def _push_plan(arena, slot_index, slot_off, runs, itemsize, device_index):
+    """Copy plan that stores this rank's contiguous panels into the same slot of every peer (one launch, SM stores over NVLink)."""
+    import numpy as np
+    from . import plans
+    key = (id(runs), slot_index, itemsize)
+    ent = _plans_push.get(key)
+    if ent is None or ent[0] is not runs:
+        recs = []
+        for peer_rank in range(arena.world):
+            if peer_rank == arena.rank:
+                continue
+            sh = arena.shift(peer_rank, itemsize)
+            for lo, hi in runs[arena.rank]:
+                pos = lo
+                while pos < hi:                     # records stay below 2^31 elements
+                    n = min(hi - pos, (1 << 30))
+                    recs.append([pos, pos + sh, n, 1, 1])
+                    pos += n
+        plan = plans.CopyPlan(np.array(recs, dtype=np.int64).reshape(len(recs), 5), 1, itemsize, device_index) if recs else None
+        if len(_plans_push) > 4096:
+            _plans_push.clear()
+        ent = (runs, plan)
+        _plans_push[key] = ent
+    return ent[1]
+
+
+def _exchange_arena(merged, arena, slot_index, slot_off, runs):
+    """``merged`` is this rank's slot: push the panels computed here into the slot of every peer, then publish."""
+    import ctypes
+    import time
+    prof = _state["profile"]
+    if prof:
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+    plan = _push_plan(arena, slot_index, slot_off, runs, merged.element_size(), merged.device.index)
+    if plan is not None:
+        st = ctypes.c_void_p(torch.cuda.current_stream(merged.device).cuda_stream)
+        plan.run(merged.data_ptr(), merged.data_ptr(), merged.numel(), 0, st)
+    arena.publish()
+    _state["stats"]["allreduce_bytes"] += sum(hi - lo for lo, hi in runs[arena.rank]) * merged.element_size() * (arena.world - 1)
+    if prof:
+        torch.cuda.synchronize()
+        _state["stats"]["allreduce_s"] += time.perf_counter() - t0
+
+
 def _stage_for(rank, world, order_a, mm_a, mn_a, size_a, order_b, mm_b, mn_b, size_b, meta_dot, size_m, meta_unmerge):
     stage = {"merge_a": None if mm_a is None else {"order": order_a, "meta_new": mn_a, "meta_mrg": mm_a, "Dsize": size_a},
              "merge_b": None if mm_b is None else {"order": order_b, "meta_new": mn_b, "meta_mrg": mm_b, "Dsize": size_b},
@@ -102,7 +170,7 @@ def _merge_part(data, m):
     return _bk.transpose_and_merge_partial(data, m["order"], m["meta_new"], m["meta_mrg"], m["Dsize"])
 
 
-def enable(group=None, min_flops=None):
+def enable(group=None, min_flops=None, peer_arena=True):
     """Shard the large contractions and the decompositions of every YASTN call made from now on over the ranks of ``group``
     (default: the world group of an initialised torch.distributed).  Every rank must run the same program."""
     import torch.distributed as dist
@@ -114,6 +182,7 @@ def enable(group=None, min_flops=None):
     _state.update(group=group, rank=dist.get_rank(group), world=dist.get_world_size(group))
     if min_flops is not None:
         _state["min_flops"] = float(min_flops)
+    _arena["disabled"] = not peer_arena          # False: NCCL broadcasts instead of peer-memory stores (also the gloo / CPU path)
     decomp.set_spmd(all_reduce_ if _state["world"] > 1 else None, _state["rank"], _state["world"])
     if _state["saved_f2m"] is not None or _state["world"] == 1:
         return
@@ -181,10 +250,19 @@ def enable(group=None, min_flops=None):
             _bk._recorder.unsupported("collective")      # a chain must never replay this without its exchange
         data_a = da if stage["merge_a"] is None else _merge_part(da, stage["merge_a"])
         data_b = db if stage["merge_b"] is None else _merge_part(db, stage["merge_b"])
-        merged = torch.empty(struct_m.size, dtype=da.dtype, device=da.device)
-        _bk.dot_into(data_a, data_b, stage["dot"]["meta_dot"], merged)
-        exchange_(merged, runs)
-        out = merged if meta_unmerge is None else backend.unmerge(merged, meta_unmerge)
+        if da.is_cuda and not _arena["disabled"]:
+            # the merged result lives in a peer-mapped slot: every rank stores its panels into all peers' slots with one
+            # launch of the copy kernel (350-560 GB/s per rank over NVLink, §3.4), a one-element all-reduce publishes them
+            arena, k, off = _arena_slot(struct_m.size * da.element_size(), da.device)
+            merged = arena.view(off, struct_m.size, da.dtype)
+            _bk.dot_into(data_a, data_b, stage["dot"]["meta_dot"], merged)
+            _exchange_arena(merged, arena, k, off, runs)
+            out = merged.clone() if meta_unmerge is None else backend.unmerge(merged, meta_unmerge)     # leaves the slot
+        else:
+            merged = torch.empty(struct_m.size, dtype=da.dtype, device=da.device)
+            _bk.dot_into(data_a, data_b, stage["dot"]["meta_dot"], merged)
+            exchange_(merged, runs)
+            out = merged if meta_unmerge is None else backend.unmerge(merged, meta_unmerge)
         if _state["profile"] and da.is_cuda:
             torch.cuda.synchronize()
             st["sharded_s"] += time.perf_counter() - t0
@@ -207,3 +285,7 @@ def disable():
         _state["saved_f2m"] = None
     _state.update(group=None, rank=0, world=1)
     _plans.clear()
+    _plans_push.clear()
+    if _arena["arena"] is not None:
+        _arena["arena"].close()
+        _arena.update(arena=None, slot_bytes=0, next=0)
