@@ -6,7 +6,9 @@ The package holds exactly what that path needs:
   plans.py          translation of YASTN's host metadata tuples into device plan tables, and the plan cache
   backend_b200.py   the drop-in backend functions (same names/signatures as yastn.backend.backend_torch)
   yastn_backend.py  the backend module object / activate() that plugs those functions into an unmodified YASTN
-  decomp.py         sector-parallel svd / qr / eigh schedule
+  decomp.py, cusolver_svdp.py   sector decompositions: batched Jacobi kernel, gesvdp, sector-parallel schedule
+  chain.py          several tensordots in a row (Heff2, environment updates) recorded once, replayed by one library call
   sharding.py, peer.py   multi-GPU sector sharding and the NVLink peer-arena block exchange
+  spmd.py           an unmodified YASTN program on several GPUs: sharded contractions and decompositions, replicated tensors
 """
-__version__ = "0.2.0"
+__version__ = "0.3.0"

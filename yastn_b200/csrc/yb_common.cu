@@ -65,7 +65,25 @@ int recycle_pending(DevicePool& p) {     // p.mu held
 
 cudaError_t new_slab(DevicePool& p) {    // p.mu held; the rest of the previous slab is abandoned (less than one block)
     void* slab = nullptr;
-    cudaError_t err = cudaMalloc(&slab, kSlabBytes);
+    // stream-ordered allocation on the pool's private stream: a plain cudaMalloc waits for the kernels queued on every stream
+    // (95-110 ms stalls in the middle of a D = 4096 sweep, profiles/plan_trace_hubbard_r02.jsonl)
+    cudaError_t err = cudaErrorNotSupported;
+    if (!p.copy_stream) {
+        if (cudaStreamCreateWithFlags(&p.copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&p.copy_done, cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            p.copy_stream = nullptr;
+        }
+    }
+    if (p.copy_stream) {
+        err = cudaMallocAsync(&slab, kSlabBytes, p.copy_stream);
+        if (err == cudaSuccess) err = cudaStreamSynchronize(p.copy_stream);
+        if (err != cudaSuccess) {
+            cudaGetLastError();
+            slab = nullptr;
+        }
+    }
+    if (err != cudaSuccess) err = cudaMalloc(&slab, kSlabBytes);
     if (err != cudaSuccess) return err;
     p.slab = (char*)slab;
     p.slab_used = 0;
