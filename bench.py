@@ -26,7 +26,8 @@ gpu_baseline = the reference's stock torch backend on the same GPU (loop of cuBL
          yastn/backend/_backend_torch_backwards.py:100-109,340-364,397-408) through yastn.tensordot, and our backend module
          through the very same yastn.tensordot calls.
 dmrg_sweep_s = one 2-site DMRG sweep of the U(1)xU(1) Hubbard chain at D=4096 complex128 (BASELINE config 3 shape, N=20 sites)
-         on the unmodified YASTN with our backend module and with the stock torch backend on the same GPU.
+         on the unmodified YASTN with our backend module (fused dot+unmerge, recorded tensordot chains) and with the stock torch
+         backend on the same GPU.  N > 1 adds spmd_dmrg_sweep: the same sweep run SPMD on all ranks (yastn_b200.spmd).
 """
 import argparse
 import json
@@ -287,7 +288,7 @@ def dmrg_sweep_spmd(rank, world, timeout=900):
     env = dict(os.environ)
     env["MASTER_PORT"] = str(int(env.get("MASTER_PORT", "29500")) + 23)
     cmd = [sys.executable, os.path.join(ROOT, "tools", "dmrg_bench.py"), "--model", "hubbard", "--N", "20", "--D", "4096", "--D0", "4096",
-           "--sweeps", "1", "--dtype", "complex128", "--backend", "b200", "--fused", "--spmd"]
+           "--sweeps", "1", "--dtype", "complex128", "--backend", "b200", "--fused", "--chains", "--spmd"]
     try:
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
         if rank != 0:
@@ -303,7 +304,7 @@ def dmrg_sweep_spmd(rank, world, timeout=900):
 def dmrg_sweep(which, timeout=900):
     """One 2-site DMRG sweep, U(1)xU(1) Hubbard N=20 D=4096 complex128, in a fresh process (tools/dmrg_bench.py)."""
     cmd = [sys.executable, os.path.join(ROOT, "tools", "dmrg_bench.py"), "--model", "hubbard", "--N", "20", "--D", "4096", "--D0", "4096",
-           "--sweeps", "1", "--dtype", "complex128", "--backend", which] + (["--fused", "--gemm-roofline"] if which == "b200" else [])
+           "--sweeps", "1", "--dtype", "complex128", "--backend", which] + (["--fused", "--chains", "--gemm-roofline"] if which == "b200" else [])
     try:
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
         line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]

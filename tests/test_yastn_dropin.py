@@ -334,6 +334,19 @@ def test_vector_ops_run_on_the_elementwise_engine(device, dtype):
     close(U @ S @ V, u @ s @ v, tol=1e-11)
 
 
+def test_flip_charges_mask_given_as_slice(device):
+    """yastn.flip_charges permutes whole blocks through embed_mask with ``mask = {0: slice(None)}`` (yastn/tensor/_single.py:224):
+    a mask may be a slice, not only an index vector (found by the reference's test_fuse_hard.py::test_initialize_eye)."""
+    ref, our = cfgs("U1", "fuse_to_matrix", device)
+    ref.backend.random_seed(5)
+    a, _ = u1_operands(ref, "float64")
+    A = mirror(a, our)
+    n0 = yastn_backend.call_counts()["native"]["embed_mask"]
+    for axes in ((1,), (0, 2), (1, 2, 3)):
+        close(A.flip_charges(axes=axes), a.flip_charges(axes=axes))
+    assert yastn_backend.call_counts()["native"]["embed_mask"] - n0 == 3
+
+
 def test_swap_gate_negates_blocks_natively(device):
     """Fermionic swap gates (negate_blocks; every CTM move of a fermionic PEPS): one launch, bit-exact."""
     ref = yastn.make_config(sym="Z2", backend="np", fermionic=True)

@@ -633,17 +633,27 @@ def _mask_index(mask, order, device):
     return idx[0].contiguous() if len(idx) == 1 else torch.cat(idx)
 
 
+def _whole_blocks(mask):
+    """True when every mask entry is ``slice(None)``: yastn.flip_charges moves whole blocks through embed_mask with
+    ``mask = {0: slice(None)}`` (yastn/tensor/_single.py:224)."""
+    vals = list(mask.values())
+    return bool(vals) and all(isinstance(v, slice) and v == slice(None) for v in vals)
+
+
 def _mask_run(data, mask, meta, Dsize, axis, ndim, scatter):
     """GATHER (scatter=False) / SCATTER (True) of the records of ``meta``; SCATTER leaves the unselected positions zero."""
-    key = ("mask", id(meta), axis, ndim, scatter, data.dtype, data.device.index)
+    whole = _whole_blocks(mask)
+    key = ("mask", id(meta), axis, ndim, scatter, whole, data.dtype, data.device.index)
 
     def build():
+        if whole:
+            return {"fwd": plans.EwPlan(plans.block_copy_tables(meta), _ITEMSIZE[data.dtype], data.device.index), "order": None}
         recs, order = plans.mask_tables(meta, axis, ndim, scatter)
         return {"fwd": plans.EwPlan(recs, _ITEMSIZE[data.dtype], data.device.index), "order": order}
     ent = _CACHE.get(key, meta, build)
     out = (torch.zeros if scatter else torch.empty)(Dsize, dtype=data.dtype, device=data.device)
     if len(meta):
-        _run_ew(ent["fwd"], out, [_plain(data, data.dtype)], _mask_index(mask, ent["order"], data.device))
+        _run_ew(ent["fwd"], out, [_plain(data, data.dtype)], None if whole else _mask_index(mask, ent["order"], data.device))
     return out
 
 

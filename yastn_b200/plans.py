@@ -635,6 +635,19 @@ def mask_tables(meta, axis, ndim, scatter):
     return _ew_array(recs), tuple(order)
 
 
+def block_copy_tables(meta):
+    """LINCOMB records of apply_mask / embed_mask whose mask is ``slice(None)`` for every charge (yastn.flip_charges,
+    yastn/tensor/_single.py:220-225): every record moves a whole block, ``new[sln] = A[sla]``."""
+    recs = []
+    for sln, Dn, sla, Da, _ in meta:
+        n = sln[1] - sln[0]
+        if n != sla[1] - sla[0]:
+            raise ValueError("mask slice(None): source and destination blocks differ in size")
+        if n > 0:
+            recs.append(_ew_rec(EW_LINCOMB, sln[0], n, [sla[0]], 0))
+    return _ew_array(recs)
+
+
 def trace_tables(order, meta):
     """TRACE records of backend.trace (yastn/backend/backend_torch.py:268-275):
     ``new[sln] += sum_i data[slo].reshape(Do).permute(order).reshape(D, D, rest)[i, i, :]``."""

@@ -152,10 +152,21 @@ def _make_hot(stock_fns, delegate):
     def dot_diag(Adata, Bdata, meta, Dsize, axis, a_ndim):
         return ewise("dot_diag", (Adata, Bdata), (Adata, Bdata, meta, Dsize, axis, a_ndim), True)
 
+    def _partial_slices(mask):
+        """Masks given as slices other than slice(None) (no caller in the reference) keep the reference's code."""
+        return any(isinstance(v, slice) and v != slice(None) for v in mask.values()) or \
+            (any(isinstance(v, slice) for v in mask.values()) and not all(isinstance(v, slice) for v in mask.values()))
+
     def apply_mask(Adata, mask, meta, Dsize, axis, ndim):
+        if _partial_slices(mask):
+            delegated["apply_mask"] += 1
+            return stock_fns["apply_mask"](Adata, mask, meta, Dsize, axis, ndim)
         return ewise("apply_mask", (Adata,), (Adata, mask, meta, Dsize, axis, ndim), False)
 
     def embed_mask(Adata, mask, meta, Dsize, axis, ndim):
+        if _partial_slices(mask):
+            delegated["embed_mask"] += 1
+            return stock_fns["embed_mask"](Adata, mask, meta, Dsize, axis, ndim)
         return ewise("embed_mask", (Adata,), (Adata, mask, meta, Dsize, axis, ndim), False)
 
     def trace(data, order, meta, Dsize):
