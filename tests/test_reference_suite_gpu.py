@@ -51,7 +51,7 @@ def test_reference_contraction_tests_other_policies(policy):
     assert d["failed"] == 0, d["failed_ids"]
     assert d["passed"] >= 40
     native = d["hot_calls"]["native"]
-    assert (native["transpose_dot_sum"] if policy == "no_fusion" else native["dot"]) > 1000
+    assert (native["transpose_dot_sum"] if policy == "no_fusion" else native["dot"]) > 100
 
 
 def test_reference_mps_tests_with_recorded_chains():

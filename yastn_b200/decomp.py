@@ -28,7 +28,9 @@ from concurrent.futures import ThreadPoolExecutor
 import numpy as np
 import torch
 
-_WORKERS = int(os.environ.get("YASTN_B200_DECOMP_WORKERS", "8"))
+# 4 sector streams: with gesvdp a D=4096 complex128 sweep takes 12.0-12.3 s at 4, 13.3-14.0 at 8, 14.4 at 12, 15.6 at 16 and 16.1 at 2
+# (profiles/decomp_workers_r02.jsonl; round 1's gesvd wanted 8: the slower routine left more of the GPU idle per stream)
+_WORKERS = int(os.environ.get("YASTN_B200_DECOMP_WORKERS", "4"))
 # Per-sector SVD routine.  "gesvd" is the reference's choice on CUDA (torch_svd_gesdd.py:17) and gives U, S, Vh bit-identical to
 # the stock torch backend.  The default "gesvdp" sends sectors of at least _SVDP_MIN rows and columns to cuSOLVER's
 # polar-decomposition SVD (yastn_b200/cusolver_svdp.py): 26 vs 87 ms for a 652 x 652 complex128 sector, 5.6 vs 15.4 ms at 163,
