@@ -185,6 +185,39 @@ def test_operands_sharing_data_are_part_of_the_key(device):
     assert chain.stats()["chains"] == 2
 
 
+def test_ctmrg_double_layer_contractions_replay_bit_exact(device):
+    """chain.enable_peps(): append_vec_* of the CTMRG double-layer contractions (yastn/tn/fpeps/envs/_env_contractions.py:211-365)
+    traced as they stand; a CTM run with chains reproduces the environment of the plain run bit for bit."""
+    import yastn.tn.fpeps as fpeps
+
+    def run(use):
+        cfg = yastn.make_config(sym="U1", backend=yastn_backend.module(), default_device=device, tensordot_policy="fuse_to_matrix")
+        cfg.backend.random_seed(0)
+        lv = yastn.gaussian_leg(cfg, s=1, n=0, sigma=1.0, D_total=3, method="round")
+        lp = yastn.Leg(cfg, s=1, t=(-1, 1), D=(1, 1))
+        A = yastn.rand(cfg, legs=[lv.conj(), lv, lv, lv.conj(), lp], n=0)
+        A = A / A.norm()
+        psi = fpeps.Peps(geometry=fpeps.SquareLattice(dims=(1, 1), boundary="infinite"), tensors={(0, 0): A})
+        env = fpeps.EnvCTM(psi, init="eye")
+        if use:
+            chain.enable_peps()
+            chain.clear()
+        try:
+            env.ctmrg_(opts_svd={"D_total": 8, "tol": 1e-12}, max_sweeps=5, corner_tol=1e-14)
+            st = chain.stats()
+        finally:
+            chain.disable()
+        e = env[(0, 0)]
+        return [_bits(getattr(e, k)) for k in ("tl", "t", "tr", "r", "br", "b", "bl", "l")], st
+    yastn_backend.enable_fused_tensordot()
+    s0 = chain.stats()
+    plain, _ = run(False)
+    chained, st = run(True)
+    assert st["replayed"] - s0["replayed"] >= 8 and st["rejected"] == s0["rejected"]
+    for x, y in zip(plain, chained):
+        assert np.array_equal(x, y)
+
+
 def test_chain_abi_rejects_malformed_steps():
     lib = _lib.load()
     h = ctypes.c_void_p()

@@ -55,10 +55,11 @@ def test_reference_contraction_tests_other_policies(policy):
 
 
 def test_reference_mps_tests_with_recorded_chains():
-    """The reference's DMRG / TDVP / environment tests with Heff1, Heff2 and the environment updates replayed from recorded chains
-    (yastn_b200.chain) and dot + unmerge fused: no failures, and the chains really replay."""
-    d, _ = _run("fuse_to_matrix", ["mps/test_dmrg.py", "mps/test_tdvp.py", "mps/test_env.py", "mps/test_environment.py", "mps/test_measurement.py"],
-                extra=("--chains",))
+    """The reference's DMRG / TDVP / environment / CTMRG tests with Heff1, Heff2, the environment updates and the double-layer
+    PEPS contractions replayed from recorded chains (yastn_b200.chain) and dot + unmerge fused: no failures, and the chains
+    really replay."""
+    d, _ = _run("fuse_to_matrix", ["mps/test_dmrg.py", "mps/test_tdvp.py", "mps/test_env.py", "mps/test_environment.py", "mps/test_measurement.py",
+                                   "peps/test_ctmrg.py"], extra=("--chains",))
     assert d["failed"] == 0, d["failed_ids"]
     assert d["passed"] >= 10
     assert d["chains"]["replayed"] > d["chains"]["recorded"] > 0

@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--dtype", default="float64")
     ap.add_argument("--policy", default="fuse_to_matrix")
     ap.add_argument("--fused", action="store_true")
+    ap.add_argument("--chains", action="store_true", help="b200 only: record / replay the double-layer contractions (yastn_b200.chain.enable_peps)")
     ap.add_argument("--decomp-workers", type=int, default=None, help="b200 only: sector streams of svd/qr/eigh (1 = the reference's serial loop)")
     ap.add_argument("--profile", action="store_true", help="time every backend function (device-synchronised: perturbs the totals)")
     ap.add_argument("--shim", action="store_true", help="CPU table interpreter instead of the kernels (host-logic check, tests/cpu_shim.py)")
@@ -56,6 +57,9 @@ def main():
         counts = yastn_backend.call_counts
         if args.fused:
             yastn_backend.enable_fused_tensordot()
+        if args.chains:
+            from yastn_b200 import chain
+            chain.enable_peps()
     else:
         backend = args.backend
     prof = {}
@@ -84,8 +88,10 @@ def main():
         dsv.append(float(info.max_dsv) if info.max_dsv is not None else None)
     chi_reached = max(max(env[(0, 0)].tl.get_shape()), max(env[(0, 0)].t.get_shape()))
     line = {"model": "ctmrg_U1", "D": args.D, "chi": args.chi, "chi_reached": int(chi_reached), "dtype": args.dtype,
-            "backend": args.backend + ("+fused" if args.fused else "") + ("+shim" if args.shim else ""), "device": device,
+            "backend": args.backend + ("+fused" if args.fused else "") + ("+chains" if args.chains else "") + ("+shim" if args.shim else ""), "device": device,
             "policy": args.policy, "sweep_s": times, "max_dsv": dsv, "hot_calls": counts() if counts else None, "decomp_workers": args.decomp_workers}
+    if args.backend == "b200" and args.chains:
+        line["chains"] = chain.stats()
     if args.profile:
         top = sorted(prof.items(), key=lambda kv: -kv[1][1])[:16]
         line["backend_profile"] = {k: {"calls": v[0], "s": round(v[1], 3)} for k, v in top}

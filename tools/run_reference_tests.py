@@ -64,6 +64,7 @@ def main():
         from yastn_b200 import chain
         yastn_backend.enable_fused_tensordot()
         chain.enable()
+        chain.enable_peps()
     lines = []
     for policy in args.policies:
         before = yastn_backend.call_counts()

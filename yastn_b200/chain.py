@@ -14,7 +14,8 @@ scratch arena (intermediates share it by lifetime) and replay all launches with 
 no per-step Python.  Anything else (a torch operation between the steps, an elementwise plan, inputs that require grad, an
 empty result) is never replayed: ``fn`` simply runs as the reference would run it.
 
-``enable()`` installs chains for ``Env_mps_mpo_mps.Heff1 / Heff2 / update_env_to_last / update_env_to_first``; the chain can
+``enable()`` installs chains for ``Env_mps_mpo_mps.Heff1 / Heff2 / update_env_to_last / update_env_to_first``, ``enable_peps()``
+for the double-layer contractions of CTMRG (``append_vec_*``, yastn/tn/fpeps/envs/_env_contractions.py:211-365); the chain can
 additionally be replayed from a CUDA graph (``YASTN_B200_CHAIN_GRAPH=1``: operands are staged into static buffers, one graph
 launch per application) — measured slower than the direct replay at every size, see DESIGN.md.
 """
@@ -319,10 +320,65 @@ def enable():
     cls.update_env_to_last, cls.update_env_to_first = update_env_to_last, update_env_to_first
 
 
+_PEPS_FNS = ("append_vec_tl", "append_vec_br", "append_vec_tr", "append_vec_bl")
+_saved_peps = {}
+
+
+def enable_peps():
+    """Chains for the double-layer contractions of CTMRG: ``append_vec_tl / _br / _tr / _bl``
+    (yastn/tn/fpeps/envs/_env_contractions.py:211-365, reached from ``DoublePepsTensor.tensordot``,
+    yastn/tn/fpeps/_doublePepsTensor.py:246-283) attach the bra and ket PEPS tensors to a corner / edge vector through fuse_legs,
+    unfuse_legs, two tensordots and a final fuse — ~12 backend calls walked in Python for operands whose block structure is the
+    same in every CTM sweep once the environment dimension has saturated.  The reference functions themselves are traced
+    (nothing is restated); calls with an operator inserted (``op``) run as written, and on fermionic lattices the swap gates in
+    between are elementwise plans, so those recordings are rejected and the functions keep running as written."""
+    if _saved_peps:
+        return
+    import inspect
+    import sys
+    import yastn.tn.fpeps.envs._env_contractions as EC
+    import yastn.tn.fpeps  # noqa: F401  (loads the modules that imported the functions by name)
+    for name in _PEPS_FNS:
+        orig = getattr(EC, name)
+        sig = inspect.signature(orig)
+
+        def make(orig, sig, name):
+            def wrapped(*args, **kwargs):
+                b = sig.bind(*args, **kwargs)
+                b.apply_defaults()
+                a = b.arguments
+                if a.get("op") is not None:
+                    return orig(*args, **kwargs)
+                mode, in_b, out_a = a["mode"], tuple(a["in_b"]), tuple(a["out_a"])
+                keys = list(a)[:3]          # (Ac, A, vector)
+                return trace((name, mode, in_b, out_a), lambda x, y, v: orig(x, y, v, op=None, mode=mode, in_b=in_b, out_a=out_a),
+                             tuple(a[k] for k in keys))
+            wrapped.__wrapped__ = orig
+            wrapped.__doc__ = orig.__doc__
+            return wrapped
+        new = make(orig, sig, name)
+        _saved_peps[name] = (orig, new)
+    for mod in list(sys.modules.values()):
+        if mod is None or not getattr(mod, "__name__", "").startswith("yastn.tn.fpeps"):
+            continue
+        for name, (orig, new) in _saved_peps.items():
+            if getattr(mod, name, None) is orig:
+                setattr(mod, name, new)
+
+
 def disable():
     if _saved:
         import yastn.tn.mps._env as E
         for name, fn in _saved.items():
             setattr(E.Env_mps_mpo_mps, name, fn)
         _saved.clear()
+    if _saved_peps:
+        import sys
+        for mod in list(sys.modules.values()):
+            if mod is None or not getattr(mod, "__name__", "").startswith("yastn.tn.fpeps"):
+                continue
+            for name, (orig, new) in _saved_peps.items():
+                if getattr(mod, name, None) is new:
+                    setattr(mod, name, orig)
+        _saved_peps.clear()
     clear()
