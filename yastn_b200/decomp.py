@@ -28,9 +28,17 @@ from concurrent.futures import ThreadPoolExecutor
 import numpy as np
 import torch
 
-# 4 sector streams: with gesvdp a D=4096 complex128 sweep takes 12.0-12.3 s at 4, 13.3-14.0 at 8, 14.4 at 12, 15.6 at 16 and 16.1 at 2
-# (profiles/decomp_workers_r02.jsonl; round 1's gesvd wanted 8: the slower routine left more of the GPU idle per stream)
-_WORKERS = int(os.environ.get("YASTN_B200_DECOMP_WORKERS", "4"))
+# Sector streams.  Unset: 4 for complex128, 8 for float64 — with gesvdp a D=4096 complex128 sweep takes 12.0-12.3 s at 4 streams,
+# 12.6-14.0 at 8, 14.4 at 12, 15.6 at 16, 16.1 at 2; the same sweep in float64 9.8 s at 8 and 10.8 at 4; CTMRG chi=256 (float64)
+# 0.74-0.86 s at 8, 0.83-0.93 at 4 (profiles/decomp_workers_r02.jsonl).  Round 1's gesvd wanted 8 everywhere: the slower
+# routine left more of the GPU idle per stream.
+_WORKERS = int(os.environ["YASTN_B200_DECOMP_WORKERS"]) if "YASTN_B200_DECOMP_WORKERS" in os.environ else None
+
+
+def _workers(complex_data=False):
+    return _WORKERS if _WORKERS is not None else (4 if complex_data else 8)
+
+
 # Per-sector SVD routine.  "gesvd" is the reference's choice on CUDA (torch_svd_gesdd.py:17) and gives U, S, Vh bit-identical to
 # the stock torch backend.  The default "gesvdp" sends sectors of at least _SVDP_MIN rows and columns to cuSOLVER's
 # polar-decomposition SVD (yastn_b200/cusolver_svdp.py): 26 vs 87 ms for a 652 x 652 complex128 sector, 5.6 vs 15.4 ms at 163,
@@ -101,29 +109,29 @@ def _sector_svd(A, fullrank_uv):
     return torch.linalg.svd(A, full_matrices=fullrank_uv, driver=_torch_driver() if A.is_cuda else None)
 
 
-def _pool(device):
+def _pool(device, workers):
     with _pools_lock:
-        key = (device.type, device.index)
+        key = (device.type, device.index, workers)
         p = _pools.get(key)
-        if p is None or p.workers != _WORKERS:
-            if p is None and device.type == "cuda":
+        if p is None:
+            if device.type == "cuda" and not any(k[:2] == key[:2] for k in _pools):
                 _warm_linalg(device)
-            p = _Pool(device, _WORKERS)
+            p = _Pool(device, workers)
             _pools[key] = p
         return p
 
 
 def set_workers(n):
-    """Number of sector streams (1 = the reference's serial schedule)."""
+    """Number of sector streams (1 = the reference's serial schedule; None = the default: 4 for complex128, 8 for float64)."""
     global _WORKERS
-    _WORKERS = max(1, int(n))
+    _WORKERS = None if n is None else max(1, int(n))
 
 
 def stats():
     return dict(_stats)
 
 
-def run_sectors(fn, recs, costs, device):
+def run_sectors(fn, recs, costs, device, complex_data=False):
     """Call ``fn(rec)`` for every record, concurrently over the sector pool of ``device`` (heaviest first, dynamic
     dealing).  Returns when every call has been *issued* and the caller's current stream has been made to wait for all
     of them, i.e. with torch's usual stream semantics for the caller."""
@@ -131,12 +139,13 @@ def run_sectors(fn, recs, costs, device):
     if n == 0:
         return
     cuda = device.type == "cuda"
-    if not (cuda or _THREADS_WITHOUT_STREAMS) or _WORKERS <= 1 or n < _MIN_SECTORS:
+    workers = _workers(complex_data)
+    if not (cuda or _THREADS_WITHOUT_STREAMS) or workers <= 1 or n < _MIN_SECTORS:
         _stats["serial_calls"] += 1
         for rec in recs:
             fn(rec)
         return
-    pool = _pool(device)
+    pool = _pool(device, workers)
     order = sorted(range(n), key=lambda i: -costs[i])
     grad = torch.is_grad_enabled()
     if cuda:
@@ -276,7 +285,7 @@ def make(stock):
                 done = set(small) - set(redo)
                 rest = [i for i in rest if i not in done]
         recs = meta if len(rest) == len(meta) else [meta[i] for i in rest]
-        run_sectors(one, recs, [_svd_cost(m[1]) for m in recs], data.device)
+        run_sectors(one, recs, [_svd_cost(m[1]) for m in recs], data.device, data.is_complex())
         if mine is not None:
             for t in (Udata, Sdata, Vhdata):
                 _spmd["all_reduce"](t)
@@ -291,7 +300,7 @@ def make(stock):
         def one(rec):
             sl, D, slS = rec[0], rec[1], rec[4]
             Sdata[slS[0]:slS[1]].copy_(torch.linalg.svdvals(data[sl[0]:sl[1]].view(D)))
-        run_sectors(one, meta, [_svd_cost(m[1]) for m in meta], data.device)
+        run_sectors(one, meta, [_svd_cost(m[1]) for m in meta], data.device, data.is_complex())
         return Sdata
 
     def eigh(data, meta=None, sizes=(1, 1), order_by_magnitude=False, ad_decomp_reg=1.0e-12):
@@ -308,7 +317,7 @@ def make(stock):
             Udata[slU[0]:slU[1]].view(DU).copy_(U)
         mine = _my_sectors([m[1][0] ** 3 for m in meta])
         recs = meta if mine is None else [meta[i] for i in mine]
-        run_sectors(one, recs, [m[1][0] ** 3 for m in recs], data.device)
+        run_sectors(one, recs, [m[1][0] ** 3 for m in recs], data.device, data.is_complex())
         if mine is not None:
             _spmd["all_reduce"](Sdata)
             _spmd["all_reduce"](Udata)
@@ -330,7 +339,7 @@ def make(stock):
             Rdata[slR[0]:slR[1]].view(DR).copy_(sR.reshape([-1, 1]) * R)
         mine = _my_sectors([_svd_cost(m[1]) for m in meta])
         recs = meta if mine is None else [meta[i] for i in mine]
-        run_sectors(one, recs, [_svd_cost(m[1]) for m in recs], data.device)
+        run_sectors(one, recs, [_svd_cost(m[1]) for m in recs], data.device, data.is_complex())
         if mine is not None:
             _spmd["all_reduce"](Qdata)
             _spmd["all_reduce"](Rdata)
