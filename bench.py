@@ -285,7 +285,9 @@ def dmrg_sweep_spmd(rank, world, timeout=900):
     """The same DMRG sweep run SPMD on all ranks of this job (yastn_b200.spmd: contractions sharded by row panels, SVD sectors
     dealt to the ranks, results completed by NCCL all-reduces over NVLink).  Every bench rank starts one child rank (fresh
     process, own rendezvous port); rank 0 returns the child's line."""
-    env = dict(os.environ)
+    # own rendezvous: a fresh TCP store on another port, started by the child of rank 0 (torchrun's agent store must not be reused:
+    # with TORCHELASTIC_USE_AGENT_STORE the child ranks would all wait as clients of a server nobody starts)
+    env = {k: v for k, v in os.environ.items() if not k.startswith("TORCHELASTIC_")}
     env["MASTER_PORT"] = str(int(env.get("MASTER_PORT", "29500")) + 23)
     cmd = [sys.executable, os.path.join(ROOT, "tools", "dmrg_bench.py"), "--model", "hubbard", "--N", "20", "--D", "4096", "--D0", "4096",
            "--sweeps", "1", "--dtype", "complex128", "--backend", "b200", "--fused", "--chains", "--spmd"]
