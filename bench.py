@@ -281,7 +281,7 @@ def gpu_baseline(sizes, cplx, dev, flops):
     return out
 
 
-def dmrg_sweep_spmd(rank, world, timeout=900):
+def dmrg_sweep_spmd(rank, world, timeout=300):
     """The same DMRG sweep run SPMD on all ranks of this job (yastn_b200.spmd: contractions sharded by row panels, SVD sectors
     dealt to the ranks, results completed by NCCL all-reduces over NVLink).  Every bench rank starts one child rank (fresh
     process, own rendezvous port); rank 0 returns the child's line."""

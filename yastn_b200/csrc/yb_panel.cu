@@ -57,7 +57,10 @@ __device__ __forceinline__ double2 pn_conj(double2 v, bool c) { return c ? make_
 template <bool CPLX, int XT, int KT>
 __global__ void __launch_bounds__(kPnThreads) panel_kernel(const PnArgs g) {
     using T = typename PnT<CPLX>::T;
-    constexpr int U = CPLX ? 2 : 4;
+    // independent columns per lane: enough loads in flight (>= 128 bytes per lane for the KT x U operand elements) without
+    // spilling the XT x U accumulators
+    constexpr int kUk = (CPLX ? 8 : 16) / KT, kUx = (CPLX ? 16 : 32) / XT;
+    constexpr int U = kUk < kUx ? (kUk < 1 ? 1 : kUk) : (kUx < 1 ? 1 : kUx);
     __shared__ T smat[kPnWarps][XT * KT];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     T* S = smat[warp];
@@ -144,12 +147,22 @@ __global__ void __launch_bounds__(kPnThreads) panel_kernel(const PnArgs g) {
     }
 }
 
-struct PanelPlan {
-    bool cplx = false;
-    int device = 0;
+// Problems are bucketed by the padded shape (XT, KT) of their small matrix: a 1 x 1 MPO block inside a launch specialised for
+// 4 x 4 would load every operand element four times and do sixteen multiply-adds for one (the charge sectors of a U1xU1 MPO are
+// mostly 1 x 1 and 2 x 2: profiles/panel_probe_r02.jsonl).  One launch per bucket; tiny plans keep a single bucket.
+struct PanelBucket {
     int xt = 1, kt = 1;
     int nprob = 0, grid = 0;
     int64_t nparts = 0;
+    size_t prob_off = 0, pstart_off = 0;     // element offsets into the plan's tables
+};
+
+struct PanelPlan {
+    bool cplx = false;
+    int device = 0;
+    int nprob = 0;
+    int64_t nparts = 0;
+    std::vector<PanelBucket> buckets;
     DeviceTable probs, pstart;
 };
 
@@ -202,26 +215,58 @@ int panel_create(const std::vector<GemmProblem>& hp, const std::vector<GemmSegme
     plan->cplx = cplx;
     plan->device = device;
     plan->nprob = (int)which.size();
-    std::vector<PnProb> probs;
-    std::vector<int64_t> pstart;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    // padded shape of every problem; a plan whose streaming extent is small keeps ONE bucket (a launch costs more than the padding)
+    struct Shape {
+        int idx, xt, kt;
+        int64_t slen;
+    };
+    std::vector<Shape> shapes;
+    int64_t total = 0;
     int mx = 1, mk = 1;
-    int64_t parts = 0;
     for (int idx : which) {
         const GemmProblem& P = hp[(size_t)idx];
         const bool rb = P.M <= kPanelMax;
-        mx = std::max(mx, rb ? P.M : P.N);
-        for (int s = P.seg_begin; s < P.seg_end; ++s) mk = std::max(mk, hs[(size_t)s].K);
-        probs.push_back({idx, rb ? 1 : 0});
-        pstart.push_back(parts);
-        parts += ((int64_t)(rb ? P.N : P.M) + kPnPart - 1) / kPnPart;
+        int k = 1;
+        for (int sg = P.seg_begin; sg < P.seg_end; ++sg) k = std::max(k, hs[(size_t)sg].K);
+        Shape sh = {idx, p2(rb ? P.M : P.N), p2(k), (int64_t)(rb ? P.N : P.M)};
+        mx = std::max(mx, sh.xt);
+        mk = std::max(mk, sh.kt);
+        total += sh.slen;
+        shapes.push_back(sh);
     }
-    pstart.push_back(parts);
-    plan->xt = p2(mx);
-    plan->kt = p2(mk);
-    plan->nparts = parts;
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    plan->grid = (int)std::max<int64_t>(1, std::min<int64_t>((parts + kPnWarps - 1) / kPnWarps, (int64_t)sms * 4));
+    const bool split = total >= (int64_t)1 << 18;
+    if (!split)
+        for (auto& sh : shapes) {
+            sh.xt = mx;
+            sh.kt = mk;
+        }
+    std::stable_sort(shapes.begin(), shapes.end(), [](const Shape& a, const Shape& b) { return a.xt != b.xt ? a.xt < b.xt : a.kt < b.kt; });
+    std::vector<PnProb> probs;
+    std::vector<int64_t> pstart;
+    for (size_t i = 0; i < shapes.size();) {
+        PanelBucket bk;
+        bk.xt = shapes[i].xt;
+        bk.kt = shapes[i].kt;
+        bk.prob_off = probs.size();
+        bk.pstart_off = pstart.size();
+        int64_t parts = 0;
+        size_t j = i;
+        for (; j < shapes.size() && shapes[j].xt == bk.xt && shapes[j].kt == bk.kt; ++j) {
+            const GemmProblem& P = hp[(size_t)shapes[j].idx];
+            probs.push_back({shapes[j].idx, P.M <= kPanelMax ? 1 : 0});
+            pstart.push_back(parts);
+            parts += (shapes[j].slen + kPnPart - 1) / kPnPart;
+        }
+        pstart.push_back(parts);
+        bk.nprob = (int)(j - i);
+        bk.nparts = parts;
+        bk.grid = (int)std::max<int64_t>(1, std::min<int64_t>((parts + kPnWarps - 1) / kPnWarps, (int64_t)sms * 4));
+        plan->nparts += parts;
+        plan->buckets.push_back(bk);
+        i = j;
+    }
     TableBatch up;
     up.add(plan->probs, probs.data(), probs.size() * sizeof(PnProb));
     up.add(plan->pstart, pstart.data(), pstart.size() * sizeof(int64_t));
@@ -237,19 +282,24 @@ int panel_create(const std::vector<GemmProblem>& hp, const std::vector<GemmSegme
 int panel_run(const PanelPlan* plan, const GemmProblem* problems, const GemmSegment* segs, const ScatterTables& scat, const void* A,
               const void* B, void* C, int flags, cudaStream_t st) {
     if (plan->nparts == 0) return kOk;
-    PnArgs a;
-    a.probs = (const PnProb*)plan->probs.ptr;
-    a.pstart = (const int64_t*)plan->pstart.ptr;
-    a.problems = problems;
-    a.segs = segs;
-    a.scat = scat;
-    a.A = (const char*)A;
-    a.B = (const char*)B;
-    a.C = (char*)C;
-    a.nprob = plan->nprob;
-    a.nparts = plan->nparts;
-    a.flags = flags;
-    return plan->cplx ? launch_x<true>(plan->xt, plan->kt, plan->grid, a, st) : launch_x<false>(plan->xt, plan->kt, plan->grid, a, st);
+    for (const PanelBucket& bk : plan->buckets) {
+        if (bk.nparts == 0) continue;
+        PnArgs a;
+        a.probs = (const PnProb*)plan->probs.ptr + bk.prob_off;
+        a.pstart = (const int64_t*)plan->pstart.ptr + bk.pstart_off;
+        a.problems = problems;
+        a.segs = segs;
+        a.scat = scat;
+        a.A = (const char*)A;
+        a.B = (const char*)B;
+        a.C = (char*)C;
+        a.nprob = bk.nprob;
+        a.nparts = bk.nparts;
+        a.flags = flags;
+        int rc = plan->cplx ? launch_x<true>(bk.xt, bk.kt, bk.grid, a, st) : launch_x<false>(bk.xt, bk.kt, bk.grid, a, st);
+        if (rc != kOk) return rc;
+    }
+    return kOk;
 }
 
 void panel_destroy(PanelPlan* plan) {
