@@ -73,6 +73,7 @@ def _on_device(dev, launch):
 
 
 _recorder = None        # yastn_b200.chain._Recorder while a chain of launches is being recorded
+_gemm_hook = None       # tools/dmrg_bench.py --gemm-roofline: called with None before a grouped-GEMM launch, with its token after
 
 
 def _run_copy(plan, src, dst, zero):
@@ -89,6 +90,11 @@ def _run_gemm(plan, A, B, C, conj_a=False, conj_b=False):
     flags = (_lib.YB_GEMM_CONJ_A if (ca != conj_a) else 0) | (_lib.YB_GEMM_CONJ_B if (cb != conj_b) else 0)
     if _recorder is not None:
         _recorder.gemm(plan, ra, rb, C, flags)
+    if _gemm_hook is not None:        # measurement tools: CUDA events right around the launch (plan creation stays outside)
+        token = _gemm_hook(None)
+        _on_device(C.device, lambda st: plan.run(ra.data_ptr(), rb.data_ptr(), C.data_ptr(), flags, st))
+        _gemm_hook(token)
+        return
     _on_device(C.device, lambda st: plan.run(ra.data_ptr(), rb.data_ptr(), C.data_ptr(), flags, st))
 
 
