@@ -298,7 +298,7 @@ def dmrg_sweep_spmd(rank, world, timeout=300):
         d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
         return {"sweep_s": d["sweep_s"][0], "energy": d["energy"][0], "ranks": world, "spmd": d.get("spmd"), "decomp": d.get("decomp_stats"),
                 "config": "U(1)xU(1) Hubbard N=20, 2-site DMRG, D=4096, complex128, one sweep; every rank runs the unmodified yastn program, "
-                          "tensordots above 4 GFLOP sharded by row panels + all-reduce, SVD sectors sharded + all-reduce"}
+                          "tensordots above 4 GFLOP sharded by row panels + peer-memory panel exchange, SVD sectors sharded + all-reduce"}
     except Exception as e:
         return {"unavailable": f"{type(e).__name__}: {str(e)[:200]}"} if rank == 0 else None
 
