@@ -401,6 +401,10 @@ def main():
         info = bk._merge_plans(data, m["order"], m["meta_new"], m["meta_mrg"], m["Dsize"])["fwd"].info()
         return (1 if info["records"] > info["tiled_records"] else 0) + (1 if info["tiled_records"] > 0 else 0)
 
+    # N > 1: a rank merges only the blocks its panels read; the rest of the merged buffer is never read, so it is not cleared
+    # either (the full-size call would memset the whole destination on every rank: merge time did not shrink with N in round 1)
+    merge = bk.transpose_and_merge_partial if world > 1 else bk.transpose_and_merge
+
     def contract(w, A, B, ev=None):
         """One fuse_to_matrix tensordot: merge A, merge B, grouped GEMM whose epilogue scatters into the unmerged
         block layout (3 launches; with --no-fuse the unmerge is a 4th launch, exactly the reference's call sequence)."""
@@ -410,9 +414,9 @@ def main():
         if ev is not None:
             ev[2].record()
         if ma is not None:
-            Am = bk.transpose_and_merge(A, ma["order"], ma["meta_new"], ma["meta_mrg"], ma["Dsize"]); launches[0] += w["launches_a"]
+            Am = merge(A, ma["order"], ma["meta_new"], ma["meta_mrg"], ma["Dsize"]); launches[0] += w["launches_a"]
         if mb is not None:
-            Bm = bk.transpose_and_merge(B, mb["order"], mb["meta_new"], mb["meta_mrg"], mb["Dsize"]); launches[0] += w["launches_b"]
+            Bm = merge(B, mb["order"], mb["meta_new"], mb["meta_mrg"], mb["Dsize"]); launches[0] += w["launches_b"]
         if ev is not None:
             ev[0].record()
         if fuse and st["unmerge"] is not None:
@@ -473,7 +477,8 @@ def main():
         for key in ("merge_a", "merge_b"):
             m = w["stage"][key]
             if m is not None:
-                merge_bytes += isz * (sum(x[1][1] - x[1][0] for x in m["meta_mrg"]) + m["Dsize"])
+                # read: the source blocks; written: the merged blocks of this rank (all of them at N = 1: Dsize)
+                merge_bytes += isz * (sum(x[1][1] - x[1][0] for x in m["meta_mrg"]) + sum(x[2][1] - x[2][0] for x in m["meta_new"]))
         if sk:   # every element of the two merged operands is read once; the result is a few numbers
             skinny_bytes += isz * sum(Da[0] * Da[1] + Db[0] * Db[1] for (_, _, _, Da, _, Db) in w["stage"]["dot"]["meta_dot"])
     own_flops = sum(w["flops"] for w in work)
