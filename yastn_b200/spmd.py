@@ -98,7 +98,7 @@ def _arena_slot(nbytes, device):
     if a["arena"] is None or a["slot_bytes"] < nbytes:
         if a["arena"] is not None:
             a["arena"].close()
-        slot = max(int(nbytes * 1.25), 256 << 20)
+        slot = max(int(nbytes * 1.25), 1 << 30)          # growing is collective (IPC handles are re-opened on every peer): start large
         slot = (slot + 4095) // 4096 * 4096
         a["arena"] = peer.PeerArena(2 * slot, device=device, group=_state["group"])
         a["slot_bytes"], a["next"] = slot, 0
