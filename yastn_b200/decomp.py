@@ -36,7 +36,14 @@ _WORKERS = int(os.environ["YASTN_B200_DECOMP_WORKERS"]) if "YASTN_B200_DECOMP_WO
 
 
 def _workers(complex_data=False):
-    return _WORKERS if _WORKERS is not None else (4 if complex_data else 8)
+    if _WORKERS is not None:
+        return _WORKERS
+    w = 4 if complex_data else 8
+    # SPMD (yastn_b200.spmd): every rank factorises only its share of the sectors, and every stream thread spins on the host
+    # while cuSOLVER synchronises — 8 ranks x 4 threads starve the replicated Python programs of cores (the D=4096 sweep took
+    # 16.8-22.8 s on 8 GPUs against 8.7 s on 4).  The node keeps about two ranks' worth of stream threads in total.
+    world = _spmd["world"] if _spmd["all_reduce"] is not None else 1
+    return w if world <= 2 else max(1, (2 * w) // world)
 
 
 # Per-sector SVD routine.  "gesvd" is the reference's choice on CUDA (torch_svd_gesdd.py:17) and gives U, S, Vh bit-identical to
