@@ -77,9 +77,9 @@ def _dmrg(yastn, backend):
     return float(out.energy), psi.get_bond_dimensions()
 
 
-def _worker(rank, port, ret):
+def _worker(rank, port, ret, world=WORLD):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         yastn, yastn_backend, spmd = _setup(True)
         cfg = yastn.make_config(sym="U1", backend=yastn_backend.module(), tensordot_policy="fuse_to_matrix", default_device="cpu")
@@ -126,3 +126,56 @@ def test_spmd_two_ranks_match_single_process():
     assert r0["energy"] == r1["energy"] and r0["bonds"] == r1["bonds"] == bonds
     assert abs(r0["energy"] - energy) <= 1e-12 * abs(energy)
     assert r0["stats_end"]["sharded"] > r0["stats"]["sharded"]
+
+
+def _fermion_worker(rank, port, ret, world):
+    """Z2 spinless fermions (swap gates -> negate_blocks, odd-parity blocks) on `world` ranks."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        yastn, yastn_backend, spmd = _setup(True)
+        ret[rank] = _fermion_dmrg(yastn, yastn_backend.module()) + (spmd.stats()["sharded"],)
+        spmd.disable()
+    finally:
+        dist.destroy_process_group()
+
+
+def _fermion_dmrg(yastn, backend):
+    import yastn.tn.mps as mps
+    N = 6
+    ops = yastn.operators.SpinlessFermions(sym="Z2", backend=backend, default_device="cpu", tensordot_policy="fuse_to_matrix")
+    ops.random_seed(seed=0)
+    I = mps.product_mpo(ops.I(), N)
+    terms = []
+    for n in range(N - 1):
+        terms += [mps.Hterm(-1.0, [n, n + 1], [ops.cp(), ops.c()]), mps.Hterm(-1.0, [n + 1, n], [ops.cp(), ops.c()])]
+    for n in range(N):
+        terms.append(mps.Hterm(0.2 * ((n % 3) - 1), [n], [ops.n()]))
+    H = mps.generate_mpo(I, terms)
+    psi = mps.random_mps(I, n=1, D_total=6)
+    out = mps.dmrg_(psi, H, method="2site", max_sweeps=3, opts_svd={"tol": 1e-10, "D_total": 10})
+    return float(out.energy), psi.get_bond_dimensions()
+
+
+def test_spmd_three_ranks_fermions_match_single_process():
+    """An odd number of ranks (uneven row panels, sectors dealt 3 ways) on a fermionic model: every rank ends with the same
+    energy and bond dimensions as the single-process run."""
+    world = 3
+    port = _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_fermion_worker, args=(port, ret, world), nprocs=world, join=True)
+        res = [ret[r] for r in range(world)]
+    yastn, yastn_backend, spmd = _setup(False)
+    try:
+        energy, bonds = _fermion_dmrg(yastn, yastn_backend.module())
+    finally:
+        import cpu_shim
+        from yastn_b200 import decomp
+        decomp._THREADS_WITHOUT_STREAMS = False
+        decomp.set_jacobi_max(64)
+        yastn_backend.disable_fused_tensordot()
+        cpu_shim.uninstall()
+    assert all(r[0] == res[0][0] and r[1] == res[0][1] for r in res)          # identical on every rank
+    assert res[0][2] > 0 and res[0][1] == bonds
+    assert abs(res[0][0] - energy) <= 1e-12 * abs(energy)
