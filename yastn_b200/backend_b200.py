@@ -33,6 +33,10 @@ _ITEMSIZE = {torch.float64: 8, torch.complex128: 16}
 def clear_plan_cache():
     _CACHE.clear()
     _BS_CACHE.clear()
+    import sys
+    chain = sys.modules.get(__package__ + ".chain")
+    if chain is not None:          # recorded chains keep their plans alive: dropped together with the plan cache
+        chain.clear()
 
 
 def plan_cache_stats():
