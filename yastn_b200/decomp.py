@@ -201,7 +201,7 @@ def set_jacobi_max(n):
 def _jacobi_svd(data, meta, small, Udata, Sdata, Vhdata, vectors=True):
     """Factorise the sectors ``meta[i], i in small`` in one launch, straight into the output tensors.  Returns the indices that
     must be redone by the library routine (not converged / exactly singular: the kernel reports, it never guesses)."""
-    from . import plans, _lib
+    from . import plans
     dev = data.device
     key = (id(meta), tuple(small) if len(small) < len(meta) else None, data.dtype, dev.index, vectors)
     ent = _jacobi_plans.get(key)
