@@ -61,3 +61,30 @@ def test_b200_arm_fails_loudly_without_cuda():
     r = _run(["--steps", "1"])
     assert r.returncode != 0 and r.stdout.strip() == ""
     assert "no CUDA device" in r.stderr
+
+
+def test_spmd_dmrg_children_get_their_own_rendezvous(monkeypatch):
+    """The SPMD DMRG leg of N > 1 starts one child rank per bench rank: fresh port, and none of torchrun's TORCHELASTIC_* variables
+    (with TORCHELASTIC_USE_AGENT_STORE the children would all wait as clients of a store nobody starts: a 15-minute hang once)."""
+    sys.path.insert(0, ROOT)
+    import importlib
+    bench = importlib.import_module("bench")
+    seen = {}
+
+    class Done:
+        stdout = json.dumps({"sweep_s": [1.5], "energy": [-2.0], "spmd": {"sharded": 3}, "decomp_stats": {}}) + "\n"
+
+    def fake_run(cmd, capture_output, text, timeout, env):
+        seen.update(cmd=cmd, env=env, timeout=timeout)
+        return Done()
+    monkeypatch.setattr(bench.subprocess, "run", fake_run)
+    monkeypatch.setenv("MASTER_PORT", "29500")
+    monkeypatch.setenv("TORCHELASTIC_USE_AGENT_STORE", "True")
+    monkeypatch.setenv("TORCHELASTIC_RUN_ID", "x")
+    monkeypatch.setenv("RANK", "0")
+    out = bench.dmrg_sweep_spmd(0, 4)
+    assert out["sweep_s"] == 1.5 and out["ranks"] == 4 and out["spmd"] == {"sharded": 3}
+    assert seen["env"]["MASTER_PORT"] == "29523" and seen["env"]["RANK"] == "0"
+    assert not any(k.startswith("TORCHELASTIC_") for k in seen["env"])
+    assert "--spmd" in seen["cmd"] and seen["timeout"] <= 300
+    assert bench.dmrg_sweep_spmd(1, 4) is None          # only rank 0 reports
