@@ -218,6 +218,23 @@ def test_ctmrg_double_layer_contractions_replay_bit_exact(device):
         assert np.array_equal(x, y)
 
 
+def test_degenerate_traces_are_rejected_not_replayed(device):
+    """A traced function that launches nothing (returns an operand, or a lazy transpose of it), or whose result is empty (no
+    matching charges), has no replayable data flow: it is run as written every time and gives the reference's answer."""
+    cfg = yastn.make_config(sym="U1", backend=yastn_backend.module(), default_device=device, tensordot_policy="fuse_to_matrix")
+    cfg.backend.random_seed(1)
+    a = yastn.rand(config=cfg, s=(-1, 1, 1), t=((0, 1), (0, 1), (0, 1)), D=((2, 3), (2, 3), (2, 3)))
+    b = yastn.rand(config=cfg, s=(-1, 1), t=((5, 6), (5, 6)), D=((2, 3), (2, 3)))       # shares no charge with the legs of a
+    s0 = chain.stats()
+    for _ in range(3):
+        r = chain.trace("identity", lambda x: x.transpose(axes=(1, 0, 2)), (a,))
+        assert r.get_shape() == a.transpose(axes=(1, 0, 2)).get_shape()
+        e = chain.trace("empty", lambda x, y: yastn.tensordot(x, y, axes=(2, 0)), (a, b))
+        assert e.size == 0
+    s1 = chain.stats()
+    assert s1["replayed"] == s0["replayed"] and s1["rejected"] - s0["rejected"] == 2
+
+
 def test_chain_abi_rejects_malformed_steps():
     lib = _lib.load()
     h = ctypes.c_void_p()
